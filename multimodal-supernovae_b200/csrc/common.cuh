@@ -1,0 +1,122 @@
+// Shared helpers for libmaven_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/maven_sm100.h"
+
+namespace mvn {
+
+void set_error(const char* fmt, ...);
+
+#define MVN_CHECK_ARG(cond, ...)                 \
+    do {                                         \
+        if (!(cond)) {                           \
+            mvn::set_error(__VA_ARGS__);         \
+            return MVN_E_BADARG;                 \
+        }                                        \
+    } while (0)
+
+#define MVN_UNSUPPORTED(cond, ...)               \
+    do {                                         \
+        if (!(cond)) {                           \
+            mvn::set_error(__VA_ARGS__);         \
+            return MVN_E_UNSUPPORTED;            \
+        }                                        \
+    } while (0)
+
+#define MVN_CUDA(expr)                                                              \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess) {                                                    \
+            mvn::set_error("%s -> %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return (int)_e;                                                         \
+        }                                                                           \
+    } while (0)
+
+#define MVN_LAUNCH_CHECK()                                                          \
+    do {                                                                            \
+        cudaError_t _e = cudaGetLastError();                                        \
+        if (_e != cudaSuccess) {                                                    \
+            mvn::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return (int)_e;                                                         \
+        }                                                                           \
+    } while (0)
+
+#define MVN_TRY(expr)            \
+    do {                         \
+        int _r = (expr);         \
+        if (_r != 0) return _r;  \
+    } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int num_sms();
+
+// number of row-slabs every weight-gradient style reduction is split into (partials are [kSlabs][...])
+constexpr int kSlabs = 128;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+template <int W>
+__device__ __forceinline__ float group_sum(float v) {   // sum over aligned groups of W lanes
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int W>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+
+// ---- internal launchers shared between the per-op C entry points and the fused encoder -------------
+struct GemmEpilogue {
+    const float* bias = nullptr;     // [N]
+    const float* addend = nullptr;   // [M,N] added before the activation / mask
+    const float* act_src = nullptr;  // [M,N] source for dact
+    int act = MVN_ACT_NONE;          // forward activation
+    int dact = 0;                    // 0 none, 1 relu mask (act_src>0), 2 gelu'(act_src)
+    // LayerNorm epilogue (N == tile width): Y = LN(acc+bias+addend)*gamma+beta
+    const float* gamma = nullptr;
+    const float* beta = nullptr;
+    float* xhat = nullptr;
+    float* rstd = nullptr;
+    float eps = 1e-5f;
+};
+// C[M,N] = A[M,K] * op(B):  b_is_nk: B stored [N,K] (nn.Linear weight) else B stored [K,N].
+int launch_gemm(const float* A, const float* Bm, float* C, const int32_t* n_rows_dev, int M_cap, int N, int K,
+                bool b_is_nk, const GemmEpilogue& ep, int prec, cudaStream_t st);
+// partial[s*pstride + woff + n*K+k] = sum over slab-s rows of dY[m,n]*X[m,k];  optional bias partial at boff.
+int launch_wgrad_partials(const float* dY, const float* X, const int32_t* n_rows_dev, int M_cap, int N, int K,
+                          float* partial, size_t pstride, size_t woff, long long boff, int prec, cudaStream_t st);
+// out[i] = (accumulate? out[i]:0) + sum_s partial[s*pstride + i], i < n
+int launch_reduce_partials(const float* partial, size_t pstride, size_t n, float* out, int accumulate, cudaStream_t st);
+int launch_ln_bwd(const float* dY, const float* xhat, const float* rstd, const float* gamma, float* dZ,
+                  const int32_t* n_rows_dev, int M_cap, int E, float* partial, size_t pstride, size_t goff, size_t boff,
+                  cudaStream_t st);
+int launch_embed_bwd_partials(const float* x, const int32_t* tok_src, const float* dout, const int32_t* n_rows_dev,
+                              int M_cap, int T, int E, int nband, float* partial, size_t pstride, size_t off, cudaStream_t st);
+
+}  // namespace mvn

@@ -1,0 +1,572 @@
+"""torch.autograd.Function wrappers over the C ABI (include/maven_sm100.h).
+
+PyTorch supplies device memory, the current stream and autograd bookkeeping; every arithmetic step is a kernel in
+libmaven_sm100.so.  CPU tensors raise: there is no fallback path.
+
+Parameter handling: a fused op consumes its parameters as ONE flat fp32 buffer (layout documented in the header).
+`FlatParams` re-homes a module's nn.Parameters as views into such a buffer (state_dict names and shapes are
+untouched); backward writes one flat gradient buffer and hands autograd per-parameter views of it, so
+`p.grad` ends up as views of a single allocation that the fused optimizer and the gradient all-reduce can use.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import SeqCfg, check, lib
+
+_LAUNCHES = 0          # kernels enqueued by this process through the library (bench.py reads it)
+
+
+def launches() -> int:
+    return _LAUNCHES
+
+
+def _count(n: int):
+    global _LAUNCHES
+    _LAUNCHES += n
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"maven_b200: `{name}` is on {t.device}; this path has CUDA kernels only (no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"maven_b200: `{name}` must be {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _mask_u8(mask: Optional[torch.Tensor], name="mask") -> Optional[torch.Tensor]:
+    if mask is None:
+        return None
+    if not mask.is_cuda:
+        raise RuntimeError(f"maven_b200: `{name}` is on {mask.device}; CUDA only")
+    if mask.dtype == torch.bool:
+        return mask.contiguous().view(torch.uint8)
+    return (mask != 0).contiguous().view(torch.uint8)
+
+
+# ======================================================================================================
+# flat parameter groups
+# ======================================================================================================
+class FlatParams:
+    """Keeps an ordered list of nn.Parameters as contiguous views of one fp32 CUDA buffer."""
+
+    def __init__(self, params: Sequence[torch.nn.Parameter]):
+        self.params = list(params)
+        self.sizes = [p.numel() for p in self.params]
+        self.offsets = [0]
+        for n in self.sizes:
+            self.offsets.append(self.offsets[-1] + n)
+        self.total = self.offsets[-1]
+        self.buffer: Optional[torch.Tensor] = None
+
+    def _is_bound(self) -> bool:
+        b = self.buffer
+        if b is None or not self.params:
+            return False
+        base = b.data_ptr()
+        first, last = self.params[0], self.params[-1]
+        return (first.data_ptr() == base and last.data_ptr() == base + 4 * self.offsets[-2]
+                and first.device == b.device)
+
+    def ensure(self) -> torch.Tensor:
+        """Returns the flat buffer, (re)building it if the parameters were moved or replaced."""
+        if self._is_bound():
+            base = self.buffer.data_ptr()
+            ok = all(p.data_ptr() == base + 4 * o for p, o in zip(self.params, self.offsets))
+            if ok:
+                return self.buffer
+        dev = self.params[0].device          # any device: this is storage plumbing; the kernels reject CPU tensors
+        for p in self.params:
+            if p.dtype != torch.float32:
+                raise TypeError("maven_b200: parameters must be float32 (bf16/tf32 arithmetic is selected per op, storage stays fp32)")
+        flat = torch.empty(self.total, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, o, n in zip(self.params, self.offsets, self.sizes):
+                v = flat[o:o + n].view(p.shape)
+                v.copy_(p.data)
+                p.data = v
+        self.buffer = flat
+        return flat
+
+    def grad_views(self, gflat: torch.Tensor, needs: Sequence[bool]) -> List[Optional[torch.Tensor]]:
+        return [gflat[o:o + n].view(p.shape) if need else None
+                for p, o, n, need in zip(self.params, self.offsets, self.sizes, needs)]
+
+
+# ======================================================================================================
+# whole sequence encoder  (A1-A7)
+# ======================================================================================================
+class SeqCall:
+    """Bookkeeping for one SeqEncoderFn call (kept out of the autograd argument list)."""
+    __slots__ = ("cfg", "flat", "off", "count", "group", "pidx", "div_term", "gbuf", "goff")
+
+    def __init__(self, cfg, flat, off, count, group, pidx, div_term, gbuf=None, goff=0):
+        self.cfg, self.flat, self.off, self.count, self.group, self.pidx = cfg, flat, off, count, group, pidx
+        self.div_term, self.gbuf, self.goff = div_term, gbuf, goff
+
+
+class SeqEncoderFn(torch.autograd.Function):
+    """mvn_seq_encoder_fwd / _bwd.  Inputs: x (B,T) fp32, t (B,T) fp32, mask (B,T) bool, a SeqCall, then the
+    parameters (only so that autograd routes their gradients; the kernels read the flat buffer)."""
+
+    @staticmethod
+    def forward(ctx, x, t, mask, call: SeqCall, *params):
+        L = lib()
+        x = _req(x, "x"); t = _req(t, "t")
+        if x.dim() != 2 or x.shape != t.shape:
+            raise ValueError(f"seq encoder: x and t must both be (B, T), got {tuple(x.shape)} and {tuple(t.shape)}")
+        m8 = _mask_u8(mask)
+        B, T = x.shape
+        cfg = SeqCfg.from_buffer_copy(call.cfg)
+        cfg.B, cfg.T = B, T
+        need = L.mvn_seq_param_count(ctypes.byref(cfg))
+        if need != call.count:
+            raise RuntimeError(f"maven_b200: parameter layout mismatch (library expects {need} floats, module packed {call.count}): "
+                               + lib().mvn_last_error().decode())
+        ws_bytes = L.mvn_seq_workspace_bytes(ctypes.byref(cfg))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        if cfg.agg == _lib.MVN_AGG_NONE:
+            out = torch.empty(B, T, cfg.E, dtype=torch.float32, device=x.device)
+        else:
+            out = torch.empty(B, cfg.enc_dim if cfg.enc_dim > 0 else cfg.n_out, dtype=torch.float32, device=x.device)
+        pview = call.flat[call.off:call.off + call.count]
+        check(L.mvn_seq_encoder_fwd(ctypes.byref(cfg), _p(pview), _p(call.div_term), _p(x), _p(t), _p(m8), _p(out), _p(ws), ws_bytes, _stream()),
+              "seq_encoder_fwd")
+        _count(4 + 1 + 5 * cfg.depth + 5)
+        ctx.cfg, ctx.ws, ctx.x, ctx.pview, ctx.call = cfg, ws, x, pview, call
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = lib()
+        dout = _req(dout, "grad_output")
+        call: SeqCall = ctx.call
+        if call.gbuf is not None:
+            g = call.gbuf[call.goff:call.goff + call.count]
+        else:
+            g = torch.empty(call.count, dtype=torch.float32, device=dout.device)
+        cfg = ctx.cfg
+        check(L.mvn_seq_encoder_bwd(ctypes.byref(cfg), _p(ctx.pview), _p(ctx.x), _p(dout), _p(g), _p(ctx.ws), ctx.ws.numel(), _stream()),
+              "seq_encoder_bwd")
+        _count(6 + 12 * cfg.depth + 2)
+        needs = ctx.needs_input_grad[4:]
+        grp: FlatParams = call.group
+        i0, i1 = call.pidx
+        base = grp.offsets[i0]
+        grads = []
+        for k, need in zip(range(i0, i1), needs):
+            if need:
+                o = grp.offsets[k] - base
+                grads.append(g[o:o + grp.sizes[k]].view(grp.params[k].shape))
+            else:
+                grads.append(None)
+        ctx.ws = None
+        return (None, None, None, None) + tuple(grads)
+
+
+# ======================================================================================================
+# per-op functions (standalone SelfAttention / TransformerBlock / Transformer modules, heads)
+# ======================================================================================================
+class LinearFn(torch.autograd.Function):
+    """Y = X W^T + b over the last dimension (nn.Linear)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, prec: int):
+        L = lib()
+        shp = x.shape
+        x2 = _req(x, "x").reshape(-1, shp[-1])
+        w = _req(w, "weight")
+        M, K = x2.shape
+        N = w.shape[0]
+        y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+        check(L.mvn_linear_fwd(_p(x2), _p(w), _p(b), _p(y), None, M, N, K, _lib.MVN_ACT_NONE, prec, _stream()), "linear_fwd")
+        _count(1)
+        ctx.save_for_backward(x2, w)
+        ctx.prec, ctx.has_b, ctx.shp = prec, b is not None, shp
+        return y.view(*shp[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = lib()
+        x2, w = ctx.saved_tensors
+        M, K = x2.shape
+        N = w.shape[0]
+        dy = _req(dy, "grad_output").reshape(M, N)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(M, K, dtype=torch.float32, device=dy.device)
+            check(L.mvn_linear_bwd_input(_p(dy), _p(w), _p(dx), None, None, 0, None, M, N, K, ctx.prec, _stream()), "linear_bwd_input")
+            _count(1)
+            dx = dx.view(ctx.shp)
+        if ctx.needs_input_grad[1] or (ctx.has_b and ctx.needs_input_grad[2]):
+            wsb = L.mvn_linear_bwd_weight_workspace_bytes(M, N, K)
+            ws = torch.empty(wsb, dtype=torch.uint8, device=dy.device)
+            dw = torch.empty(N, K, dtype=torch.float32, device=dy.device)
+            db = torch.empty(N, dtype=torch.float32, device=dy.device) if ctx.has_b else None
+            check(L.mvn_linear_bwd_weight(_p(dy), _p(x2), _p(dw), _p(db), None, M, N, K, 0, _p(ws), wsb, ctx.prec, _stream()), "linear_bwd_weight")
+            _count(3)
+        return dx, dw, db, None
+
+
+def linear(x, w, b=None, prec: int = 0):
+    return LinearFn.apply(x, w, b, prec)
+
+
+class LinearReluFn(torch.autograd.Function):
+    """relu(X W^T + b) (MLP heads): fused ReLU epilogue forward, mask + the two GEMMs backward."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, prec: int):
+        L = lib()
+        shp = x.shape
+        x2 = _req(x, "x").reshape(-1, shp[-1])
+        M, K = x2.shape
+        N = w.shape[0]
+        h = torch.empty(M, N, dtype=torch.float32, device=x.device)
+        check(L.mvn_linear_fwd(_p(x2), _p(_req(w, "weight")), _p(b), _p(h), None, M, N, K, _lib.MVN_ACT_RELU, prec, _stream()), "linear_fwd")
+        _count(1)
+        ctx.save_for_backward(x2, w, h)
+        ctx.prec, ctx.has_b, ctx.shp = prec, b is not None, shp
+        return h.view(*shp[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dh):
+        L = lib()
+        x2, w, h = ctx.saved_tensors
+        M, K = x2.shape
+        N = w.shape[0]
+        dh = _req(dh, "grad_output").reshape(M, N)
+        dpre = torch.empty_like(dh)
+        check(L.mvn_relu_bwd(_p(dh), _p(h), M * N, _p(dpre), _stream()), "relu_bwd")
+        dx = torch.empty(M, K, dtype=torch.float32, device=dh.device)
+        check(L.mvn_linear_bwd_input(_p(dpre), _p(w), _p(dx), None, None, 0, None, M, N, K, ctx.prec, _stream()), "linear_bwd_input")
+        wsb = L.mvn_linear_bwd_weight_workspace_bytes(M, N, K)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dh.device)
+        dw = torch.empty(N, K, dtype=torch.float32, device=dh.device)
+        db = torch.empty(N, dtype=torch.float32, device=dh.device) if ctx.has_b else None
+        check(L.mvn_linear_bwd_weight(_p(dpre), _p(x2), _p(dw), _p(db), None, M, N, K, 0, _p(ws), wsb, ctx.prec, _stream()), "linear_bwd_weight")
+        _count(5)
+        return dx.view(ctx.shp), dw, db, None
+
+
+class L2NormFn(torch.autograd.Function):
+    """x / ||x||_2 over the last dimension, no epsilon (src/models_multimodal.py:279,286,293)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        L = lib()
+        x2 = _req(x, "x").reshape(-1, x.shape[-1])
+        B, D = x2.shape
+        y = torch.empty_like(x2)
+        nrm = torch.empty(B, dtype=torch.float32, device=x.device)
+        check(L.mvn_l2norm_fwd(_p(x2), _p(y), _p(nrm), B, D, _stream()), "l2norm_fwd")
+        _count(1)
+        ctx.save_for_backward(y, nrm)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = lib()
+        y, nrm = ctx.saved_tensors
+        B, D = y.shape
+        dy2 = _req(dy, "grad_output").reshape(B, D)
+        dx = torch.empty_like(y)
+        check(L.mvn_l2norm_bwd(_p(dy2), _p(y), _p(nrm), _p(dx), B, D, _stream()), "l2norm_bwd")
+        _count(1)
+        return dx.view(dy.shape)
+
+
+class LinearResLNFn(torch.autograd.Function):
+    """Y = LayerNorm(X W^T + b + R) gamma + beta (one kernel); backward = LN-bwd, dX GEMM, dW GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, r, gamma, beta, eps: float, prec: int):
+        L = lib()
+        shp = r.shape
+        x2 = _req(x, "x").reshape(-1, x.shape[-1])
+        r2 = _req(r, "residual").reshape(-1, shp[-1])
+        M, K = x2.shape
+        N = w.shape[0]
+        y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+        xhat = torch.empty_like(y)
+        rstd = torch.empty(M, dtype=torch.float32, device=x.device)
+        check(L.mvn_linear_res_ln_fwd(_p(x2), _p(_req(w, "w")), _p(b), _p(r2), _p(gamma), _p(beta), _p(y), _p(xhat), _p(rstd), None, M, N, K,
+                                      eps, prec, _stream()), "linear_res_ln_fwd")
+        _count(1)
+        ctx.save_for_backward(x2, w, xhat, rstd, gamma)
+        ctx.prec, ctx.shp, ctx.xshape = prec, shp, x.shape
+        return y.view(shp)
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = lib()
+        x2, w, xhat, rstd, gamma = ctx.saved_tensors
+        M, K = x2.shape
+        N = w.shape[0]
+        dy = _req(dy, "grad_output").reshape(M, N)
+        dz = torch.empty_like(dy)
+        dg = torch.empty(N, dtype=torch.float32, device=dy.device)
+        dbt = torch.empty_like(dg)
+        wsb = max(L.mvn_linear_bwd_weight_workspace_bytes(M, N, K), 128 * 2 * N * 4)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dy.device)
+        check(L.mvn_layernorm_bwd(_p(dy), _p(xhat), _p(rstd), _p(gamma), _p(dz), _p(dg), _p(dbt), None, M, N, _p(ws), wsb, _stream()), "layernorm_bwd")
+        dx = torch.empty(M, K, dtype=torch.float32, device=dy.device)
+        check(L.mvn_linear_bwd_input(_p(dz), _p(w), _p(dx), None, None, 0, None, M, N, K, ctx.prec, _stream()), "linear_bwd_input")
+        dw = torch.empty(N, K, dtype=torch.float32, device=dy.device)
+        db = torch.empty(N, dtype=torch.float32, device=dy.device)
+        check(L.mvn_linear_bwd_weight(_p(dz), _p(x2), _p(dw), _p(db), None, M, N, K, 0, _p(ws), wsb, ctx.prec, _stream()), "linear_bwd_weight")
+        _count(3 + 1 + 3)
+        return dx.view(ctx.xshape), dw, db, dz.view(ctx.shp), dg, dbt, None, None
+
+
+class FFNResLNFn(torch.autograd.Function):
+    """Y = LayerNorm(relu(X W1^T + b1) W2^T + b2 + X) gamma + beta  -- the feed-forward half of a TransformerBlock."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, gamma, beta, eps: float, prec: int):
+        L = lib()
+        shp = x.shape
+        x2 = _req(x, "x").reshape(-1, shp[-1])
+        M, E = x2.shape
+        F = w1.shape[0]
+        dev = x.device
+        h = torch.empty(M, F, dtype=torch.float32, device=dev)
+        check(L.mvn_linear_fwd(_p(x2), _p(_req(w1, "w1")), _p(b1), _p(h), None, M, F, E, _lib.MVN_ACT_RELU, prec, _stream()), "linear_fwd")
+        y = torch.empty(M, E, dtype=torch.float32, device=dev)
+        xhat = torch.empty_like(y)
+        rstd = torch.empty(M, dtype=torch.float32, device=dev)
+        check(L.mvn_linear_res_ln_fwd(_p(h), _p(_req(w2, "w2")), _p(b2), _p(x2), _p(gamma), _p(beta), _p(y), _p(xhat), _p(rstd), None, M, E, F,
+                                      eps, prec, _stream()), "linear_res_ln_fwd")
+        _count(2)
+        ctx.save_for_backward(x2, w1, w2, h, xhat, rstd, gamma)
+        ctx.prec, ctx.shp = prec, shp
+        return y.view(shp)
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = lib()
+        x2, w1, w2, h, xhat, rstd, gamma = ctx.saved_tensors
+        M, E = x2.shape
+        F = w1.shape[0]
+        dev = dy.device
+        dy = _req(dy, "grad_output").reshape(M, E)
+        f32 = dict(dtype=torch.float32, device=dev)
+        wsb = max(L.mvn_linear_bwd_weight_workspace_bytes(M, F, E), 128 * 2 * E * 4)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        dz = torch.empty(M, E, **f32); dg = torch.empty(E, **f32); dbt = torch.empty(E, **f32)
+        check(L.mvn_layernorm_bwd(_p(dy), _p(xhat), _p(rstd), _p(gamma), _p(dz), _p(dg), _p(dbt), None, M, E, _p(ws), wsb, _stream()), "layernorm_bwd")
+        dw2 = torch.empty(E, F, **f32); db2 = torch.empty(E, **f32)
+        check(L.mvn_linear_bwd_weight(_p(dz), _p(h), _p(dw2), _p(db2), None, M, E, F, 0, _p(ws), wsb, ctx.prec, _stream()), "linear_bwd_weight")
+        dh = torch.empty(M, F, **f32)
+        check(L.mvn_linear_bwd_input(_p(dz), _p(w2), _p(dh), None, _p(h), 1, None, M, E, F, ctx.prec, _stream()), "linear_bwd_input")
+        dw1 = torch.empty(F, E, **f32); db1 = torch.empty(F, **f32)
+        check(L.mvn_linear_bwd_weight(_p(dh), _p(x2), _p(dw1), _p(db1), None, M, F, E, 0, _p(ws), wsb, ctx.prec, _stream()), "linear_bwd_weight")
+        dx = torch.empty(M, E, **f32)
+        check(L.mvn_linear_bwd_input(_p(dh), _p(w1), _p(dx), _p(dz), None, 0, None, M, F, E, ctx.prec, _stream()), "linear_bwd_input")
+        _count(3 + 3 + 1 + 3 + 1)
+        return dx.view(ctx.shp), dw1, db1, dw2, db2, dg, dbt, None, None
+
+
+class AttentionFn(torch.autograd.Function):
+    """Packed padding-masked attention core on qkv (M,3E) with dense plan (all B*T rows, keys masked)."""
+
+    @staticmethod
+    def forward(ctx, qkv, mask, B: int, T: int, E: int, H: int):
+        L = lib()
+        qkv2 = _req(qkv, "qkv").reshape(B * T, 3 * E)
+        m8 = _mask_u8(mask)
+        dev = qkv.device
+        cu = torch.empty(B + 1, dtype=torch.int32, device=dev)
+        tok = torch.empty(B * T, dtype=torch.int32, device=dev)
+        kv = torch.empty(B * T, dtype=torch.uint8, device=dev)
+        check(L.mvn_pack_plan(_p(m8), B, T, 0, _p(cu), _p(tok), _p(kv), _stream()), "pack_plan")
+        out = torch.empty(B * T, E, dtype=torch.float32, device=dev)
+        lse = torch.empty(B * T, H, dtype=torch.float32, device=dev)
+        scale = 1.0 / math.sqrt(E)
+        check(L.mvn_attention_fwd(_p(qkv2), _p(cu), _p(kv), _p(out), _p(lse), B, E, H, scale, 0, _stream()), "attention_fwd")
+        _count(5)
+        ctx.save_for_backward(qkv2, cu, kv, out, lse)
+        ctx.dims = (B, T, E, H, scale)
+        return out.view(B, T, E)
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = lib()
+        qkv2, cu, kv, out, lse = ctx.saved_tensors
+        B, T, E, H, scale = ctx.dims
+        dout = _req(dout, "grad_output").reshape(B * T, E)
+        dqkv = torch.empty_like(qkv2)
+        check(L.mvn_attention_bwd(_p(qkv2), _p(cu), _p(kv), _p(out), _p(lse), _p(dout), _p(dqkv), B, E, H, scale, 0, _stream()), "attention_bwd")
+        _count(1)
+        return dqkv.view(B, T, 3 * E), None, None, None, None, None
+
+
+class ConvCall:
+    __slots__ = ("module", "flat", "off", "count", "group", "pidx", "enc_dim", "normalize", "prec", "gbuf", "goff")
+
+    def __init__(self, module, flat, off, count, group, pidx, enc_dim, normalize, prec, gbuf=None, goff=0):
+        self.module, self.flat, self.off, self.count, self.group, self.pidx = module, flat, off, count, group, pidx
+        self.enc_dim, self.normalize, self.prec, self.gbuf, self.goff = enc_dim, normalize, prec, gbuf, goff
+
+
+class ConvMixerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, call, *params):
+        raise NotImplementedError("maven_b200: ConvMixer kernels are not built yet")
+
+
+class QueryPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, kv, B, T, E, H):
+        raise NotImplementedError("maven_b200: agg='attn' pooling kernel is not built yet")
+
+
+# ------------------------------------------------------------------------------------------------------
+# CLIP loss (A10/A11)
+# ------------------------------------------------------------------------------------------------------
+_DP_GROUP = None
+
+
+def set_data_parallel_group(group):
+    """Process group whose ranks shard the global batch (None = single process).  With a group set, clip_loss
+    all-gathers the embeddings (global-batch negatives) and both LSE vectors; see DESIGN.md, multi-GPU."""
+    global _DP_GROUP
+    _DP_GROUP = group
+
+
+def get_data_parallel_group():
+    return _DP_GROUP
+
+
+def _all_gather_rows(t: torch.Tensor, group) -> torch.Tensor:
+    import torch.distributed as dist
+    ws = dist.get_world_size(group)
+    out = torch.empty((ws * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+    return out
+
+
+class ClipLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, e1, e2, logit_scale, logit_bias, prec: int):
+        L = lib()
+        e1 = _req(e1, "embs1"); e2 = _req(e2, "embs2")
+        ls = _req(logit_scale.reshape(1), "logit_scale"); lb = _req(logit_bias.reshape(1), "logit_bias")
+        if e1.shape != e2.shape or e1.dim() != 2:
+            raise ValueError(f"clip_loss: embeddings must both be (N, D), got {tuple(e1.shape)} and {tuple(e2.shape)}")
+        n, D = e1.shape
+        grp = _DP_GROUP
+        if grp is not None:
+            import torch.distributed as dist
+            rank, world = dist.get_rank(grp), dist.get_world_size(grp)
+            e1_all, e2_all = _all_gather_rows(e1, grp), _all_gather_rows(e2, grp)
+        else:
+            rank, world, e1_all, e2_all = 0, 1, e1, e2
+        N, off = n * world, rank * n
+        wsb = L.mvn_clip_loss_workspace_bytes(n, N, D)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=e1.device)
+        loss = torch.empty(1, dtype=torch.float32, device=e1.device)
+        lse = torch.empty(2, n, dtype=torch.float32, device=e1.device)
+        check(L.mvn_clip_loss_fwd(_p(e1), _p(e2), _p(e1_all), _p(e2_all), n, N, D, off, _p(ls), _p(lb), _p(loss), _p(lse[0]), _p(lse[1]),
+                                  _p(ws), wsb, prec, _stream()), "clip_loss_fwd")
+        _count(4)
+        if grp is not None:
+            import torch.distributed as dist
+            lse_all = _all_gather_rows(lse.t().contiguous(), grp).t().contiguous()      # (2, N)
+            dist.all_reduce(loss, group=grp)
+        else:
+            lse_all = lse
+        ctx.save_for_backward(e1, e2, e1_all, e2_all, ls, lb, lse_all)
+        ctx.meta = (n, N, D, off, prec, logit_scale.shape, logit_bias.shape)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        L = lib()
+        e1, e2, e1_all, e2_all, ls, lb, lse_all = ctx.saved_tensors
+        n, N, D, off, prec, ls_shape, lb_shape = ctx.meta
+        g = _req(g.reshape(1), "grad_output")
+        wsb = L.mvn_clip_loss_workspace_bytes(n, N, D)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=e1.device)
+        d1 = torch.empty_like(e1); d2 = torch.empty_like(e2)
+        dls = torch.empty(1, dtype=torch.float32, device=e1.device)
+        check(L.mvn_clip_loss_bwd(_p(e1), _p(e2), _p(e1_all), _p(e2_all), n, N, D, off, _p(ls), _p(lb), _p(lse_all[0]), _p(lse_all[1]), _p(g),
+                                  _p(d1), _p(d2), _p(dls), _p(ws), wsb, prec, _stream()), "clip_loss_bwd")
+        _count(5)
+        # d loss / d logit_bias is identically zero under the two softmaxes; autograd still reports a zero tensor
+        dlb = torch.zeros(lb_shape, dtype=torch.float32, device=e1.device)
+        return d1, d2, dls.reshape(ls_shape), dlb, None
+
+
+class WeightedCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, class_w):
+        L = lib()
+        logits = _req(logits, "logits")
+        if labels.dtype != torch.int64:
+            labels = labels.long()
+        labels = labels.contiguous()
+        B, C = logits.shape
+        buf = torch.empty(2 + 2 * B, dtype=torch.float32, device=logits.device)
+        check(L.mvn_weighted_ce_fwd(_p(logits), _p(labels), _p(class_w), B, C, _p(buf), _stream()), "weighted_ce_fwd")
+        _count(2)
+        ctx.save_for_backward(logits, labels, class_w, buf)
+        return buf[0].clone().reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        L = lib()
+        logits, labels, class_w, buf = ctx.saved_tensors
+        B, C = logits.shape
+        d = torch.empty_like(logits)
+        g = _req(g.reshape(1), "grad_output")
+        check(L.mvn_weighted_ce_bwd(_p(logits), _p(labels), _p(class_w), B, C, _p(buf), _p(g), _p(d), _stream()), "weighted_ce_bwd")
+        _count(1)
+        return d, None, None
+
+
+class MSEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target):
+        L = lib()
+        pred = _req(pred, "pred").reshape(-1); target = _req(target, "target").reshape(-1)
+        if pred.numel() != target.numel():
+            raise ValueError("mse: size mismatch")
+        loss = torch.empty(1, dtype=torch.float32, device=pred.device)
+        check(L.mvn_mse_fwd(_p(pred), _p(target), pred.numel(), _p(loss), _stream()), "mse_fwd")
+        _count(1)
+        ctx.save_for_backward(pred, target)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        L = lib()
+        pred, target = ctx.saved_tensors
+        d = torch.empty_like(pred)
+        g = _req(g.reshape(1), "grad_output")
+        check(L.mvn_mse_bwd(_p(pred), _p(target), pred.numel(), _p(g), _p(d), _stream()), "mse_bwd")
+        _count(1)
+        return d, None
+
+
+def retrieval_ranks(e1: torch.Tensor, e2: torch.Tensor) -> torch.Tensor:
+    L = lib()
+    e1 = _req(e1, "embs1"); e2 = _req(e2, "embs2")
+    N, D = e1.shape
+    r = torch.empty(N, dtype=torch.int32, device=e1.device)
+    check(L.mvn_retrieval_ranks(_p(e1), _p(e2), N, D, _p(r), _stream()), "retrieval_ranks")
+    _count(1)
+    return r
