@@ -184,7 +184,8 @@ def test_seq_encoder_golden(name):
     (y * g["w"].to(dev())).sum().backward()
     for k, p in enc.named_parameters():
         ref = grads[k]
-        assert relerr(p.grad, ref) < GTOL or (p.grad.cpu() - ref).abs().max() < 1e-6, k
+        got = p.grad if p.grad is not None else torch.zeros_like(p)      # agg="pretraining" never touches `projection`
+        assert relerr(got, ref) < GTOL or (got.cpu() - ref).abs().max() < 1e-6, k
 
 
 @pytest.mark.parametrize("case", ["lc", "sp"])
