@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- CLIP training-step throughput of the B200-native path (and the CPU reference arm).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (default N=1)
+  python bench.py --impl reference --steps K --warmup W    # the reference algorithm (oracle port) on host cores
+
+A "step" is one full training step (forward + backward + RAdam) of the reference's LightCurveImageCLIP on one batch
+of synthetic data shaped like the simulated-pretrain configuration (light curve T=200 two-band E64 h8
+L5 + spectra T=220 E32 h2 L13, 1024 samples per GPU).  One JSON line goes to stdout.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (combinations, lc kwargs, sp kwargs, T_lc, T_sp)
+    "c4": dict(desc="C4 maven-pretrain shape: lightcurve(E64,h8,L5,T200,2 bands)+spectral(E32,h2,L13,T220) CLIP",
+               combinations=["lightcurve", "spectral"],
+               lc=dict(n_out=32, emb=64, heads=8, depth=5, time_norm=20583.369161312577, agg="mean"),
+               sp=dict(n_out=32, emb=32, heads=2, depth=13, time_norm=17945.142213594805, agg="mean"),
+               T_lc=200, T_sp=220),
+    "c2": dict(desc="C2 lc_5way_f1 shape: lightcurve(E32,h2,L9,T200) 5-way classifier",
+               combinations=["lightcurve"], classification=True, n_classes=5,
+               lc=dict(n_out=32, emb=32, heads=2, depth=9, time_norm=3371.17, agg="mean"), sp=None, T_lc=200, T_sp=0),
+}
+LR, WD, LOGIT_SCALE = 3.716367614864064e-05, 0.000555522900788888, 19.545966923442453
+
+
+# --------------------------------------------------------------------------------------------------
+# synthetic data, generated on the CPU with a fixed seed
+# --------------------------------------------------------------------------------------------------
+def make_seq(gen, B, T, nband, lo, hi, tmax, t0):
+    per = T // nband
+    n = torch.randint(lo, min(hi, per) + 1, (B, nband), generator=gen)
+    pos = torch.arange(per)[None, None, :]
+    valid = pos < n[:, :, None]                                             # (B, nband, per)
+    t = torch.rand(B, nband, per, generator=gen) * tmax
+    t = torch.where(valid, t, torch.full_like(t, float("inf"))).sort(dim=-1)[0]
+    t = t - t[:, :, :1] + t0
+    t = torch.where(valid, t, torch.zeros_like(t))
+    x = torch.where(valid, torch.randn(B, nband, per, generator=gen), torch.zeros(B, nband, per))
+    return x.reshape(B, T).contiguous(), t.reshape(B, T).contiguous(), valid.reshape(B, T).contiguous()
+
+
+def make_batch(wl, B, seed):
+    gen = torch.Generator().manual_seed(seed)
+    x_lc, t_lc, m_lc = make_seq(gen, B, wl["T_lc"], 2, 20, 100, 300.0, 0.0)           # sim-pretrain shape: Uniform{20..100}/band
+    if wl["sp"] is not None:
+        x_sp, t_sp, m_sp = make_seq(gen, B, wl["T_sp"], 1, 110, 220, 5500.0, 3700.0)   # valid length Uniform{110..220}
+    else:
+        x_sp = t_sp = m_sp = None
+    cls = torch.randint(0, 5, (B,), generator=gen)
+    red = torch.rand(B, generator=gen)
+    return [None, x_lc, t_lc, m_lc, x_sp, t_sp, m_sp, red, cls]
+
+
+def model_kwargs(wl, dropout):
+    kw = dict(logit_scale=LOGIT_SCALE, lr=LR, nband=2, loss="softmax", optimizer_kwargs={"weight_decay": WD},
+              combinations=wl["combinations"], transformer_kwargs={**wl["lc"], "dropout": dropout})
+    if wl["sp"] is not None:
+        kw["transformer_spectral_kwargs"] = {**wl["sp"], "dropout": dropout}
+    if wl.get("classification"):
+        kw.update(classification=True, n_classes=wl["n_classes"])
+    return kw
+
+
+def flops_per_step(wl, batch):
+    """Algorithmic FLOPs of one training step, two accountings: dense over the padded T (comparable with
+    the reference) and executed (valid tokens only).  Returned per kernel class for the executed accounting."""
+    out = {"padded_train": 0.0, "gemm": 0.0, "wgrad": 0.0, "attn_fwd": 0.0, "attn_bwd": 0.0}
+    for key, m_idx, T in (("lc", 3, wl["T_lc"]), ("sp", 6, wl["T_sp"])):
+        kw = wl[key]
+        if kw is None:
+            continue
+        E, L = kw["emb"], kw["depth"]
+        nb = batch[m_idx].sum(dim=1).double()
+        B = nb.numel()
+        out["padded_train"] += 3.0 * B * L * (24.0 * T * E * E + 4.0 * T * T * E)
+        M = nb.sum().item()
+        out["gemm"] += L * 48.0 * M * E * E            # forward GEMMs + input-gradient GEMMs
+        out["wgrad"] += L * 24.0 * M * E * E
+        n2 = (nb * nb).sum().item()
+        out["attn_fwd"] += L * 4.0 * n2 * E
+        out["attn_bwd"] += L * 10.0 * n2 * E
+    out["executed_train"] = out["gemm"] + out["wgrad"] + out["attn_fwd"] + out["attn_bwd"]
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops_sustained"], "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port (reference algorithm, fp32, dense over padded T) on host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_steps(wl, sample_B, steps, warmup, threads):
+    from oracle import maven_oracle as O
+    from maven_b200.models_multimodal import LightCurveImageCLIP
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    ref_model = LightCurveImageCLIP(**model_kwargs(wl, 0.0))        # used only as a weight initialiser (reference default init)
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in ref_model.state_dict().items()}
+    params = [v for v in sd.values() if v.requires_grad]
+    opt = torch.optim.RAdam(params, lr=LR, weight_decay=WD)
+    cfg = dict(combinations=wl["combinations"], nband=2, transformer_kwargs=wl["lc"], transformer_spectral_kwargs=wl["sp"],
+               classification=wl.get("classification", False), n_classes=wl.get("n_classes", 5))
+    batch = make_batch(wl, sample_B, seed=1234)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        loss = O.training_loss(sd, cfg, batch)
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return sample_B * len(times) / sum(times), sum(times) / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+    B = args.ref_batch
+    sps, sec = cpu_reference_steps(wl, B, args.steps, args.warmup, threads)
+    line = {"impl": "reference", "metric": "clip_train_samples_per_sec", "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "per_step_batch": B, "note": "oracle port of the reference algorithm (dense over padded T), torch CPU"},
+            "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
+                             "sample": f"{args.steps} training steps (fwd+bwd+torch RAdam) at batch {B} of the same workload"},
+            "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import ctypes
+    import torch.distributed as dist
+    from maven_b200 import _lib, ops
+    from maven_b200.models_multimodal import LightCurveImageCLIP
+    from maven_b200.transformer_utils import set_precision
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        ops.set_data_parallel_group(dist.group.WORLD)
+    L = _lib.lib()
+    wl = WORKLOADS[args.workload]
+    B = args.batch
+    torch.manual_seed(0)                                       # identical replicas on every rank
+    model = LightCurveImageCLIP(**model_kwargs(wl, args.dropout)).to(dev).train()
+    set_precision(model, args.precision)
+    opt = model.configure_optimizers()["optimizer"]
+    host = make_batch(wl, B, seed=1000 + rank)                 # each rank owns its shard of the global batch
+    pinned = [None if v is None else v.pin_memory() for v in host]
+    resident = [None if v is None else v.to(dev) for v in host]
+    h2d = sum(v.numel() * v.element_size() for v in (pinned[1:7]) if v is not None)
+    if wl.get("classification"):
+        h2d += pinned[8].numel() * pinned[8].element_size()
+    fl = flops_per_step(wl, host)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+
+    def step(batch):
+        loss = model.training_step(batch, 0)
+        loss.backward()
+        if world > 1:
+            dist.all_reduce(model.gather_grads())
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+    sync()
+
+    # one profiled step with every class timed -> kernel-class breakdown and the dominant class
+    names = ["gemm", "wgrad", "attn_fwd", "attn_bwd", "row", "loss", "optim", "conv"]
+    L.mvn_prof_enable(0xFF)
+    step(resident)
+    torch.cuda.synchronize()
+    breakdown = {}
+    for c, nme in enumerate(names):
+        ms, cnt = ctypes.c_double(), ctypes.c_longlong()
+        L.mvn_prof_read(c, ctypes.byref(ms), ctypes.byref(cnt))
+        breakdown[nme] = {"ms": round(ms.value, 4), "launches": cnt.value}
+    L.mvn_prof_enable(0)
+    top = max(("gemm", "wgrad", "attn_fwd", "attn_bwd"), key=lambda k: breakdown[k]["ms"])
+    top_id = names.index(top)
+
+    # ---- timed region: K steps, device-resident inputs, per-step CUDA events, L2 flushed between steps ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    L.mvn_prof_enable(1 << top_id)
+    launches0 = L.mvn_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sync()
+    wall0 = time.perf_counter()
+    for a, b in ev:
+        flush.fill_(1)
+        a.record()
+        step(resident)
+        b.record()
+    sync()
+    wall = time.perf_counter() - wall0
+    launches = L.mvn_launch_count() - launches0
+    ms_t, cnt_t = ctypes.c_double(), ctypes.c_longlong()
+    L.mvn_prof_read(top_id, ctypes.byref(ms_t), ctypes.byref(cnt_t))
+    L.mvn_prof_enable(0)
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+
+    # ---- e2e: pinned host batch -> H2D -> step -> D2H loss, everything inside the timed region -----------
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    last = None
+    for _ in range(args.steps):
+        batch = [None if v is None else v.to(dev, non_blocking=True) for v in pinned]
+        last = step(batch).item()                              # device->host read of the step's loss
+    e1.record()
+    sync()
+    e2e_wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    t = torch.tensor([dev_ms, e2e_wall * 1e3, float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, launches = t[0].item(), t[1].item(), int(t[2].item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    hbm, tf, src = peaks()
+    ms_per_step = dev_ms / args.steps
+    value = world * B * args.steps / (dev_ms / 1e3)
+    e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+    top_flops = fl[top]
+    ach = top_flops * args.steps / (ms_t.value / 1e3) / 1e12 if ms_t.value > 0 else 0.0
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sps, sec = cpu_reference_steps(wl, args.ref_batch, 3, 1, threads)
+        cpu = {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
+               "sample": f"3 training steps (fwd+bwd+torch RAdam) at batch {args.ref_batch} of the same workload, oracle port, fp32, dense over padded T"}
+    line = {
+        "metric": "clip_train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.precision == "fp32" else args.precision, "data": "synthetic",
+        "config": {"workload": wl["desc"], "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                   "dropout": args.dropout, "precision": args.precision,
+                   "l2": "256 MiB flush written between timed steps; per-step activation working set is GBs (>> 126 MB L2)",
+                   "valid_token_fraction": {"lc": float(host[3].float().mean()), "sp": float(host[6].float().mean()) if host[6] is not None else None}},
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel_class": top, "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf,
+                     "traffic": None, "peak_source": src, "launches_timed": cnt_t.value, "class_ms_per_step": ms_t.value / args.steps,
+                     "flops_accounting": "executed (valid tokens only); padded-equivalent step FLOPs in flops_per_step.padded_train"},
+        "flops_per_step": {k: v for k, v in fl.items()},
+        "step_tflops": {"padded_equivalent": fl["padded_train"] / (ms_per_step / 1e3) / 1e12, "executed": fl["executed_train"] / (ms_per_step / 1e3) / 1e12,
+                        "frac_of_peak_padded": fl["padded_train"] / (ms_per_step / 1e3) / 1e12 / tf},
+        "kernel_breakdown_ms": breakdown,
+        "wall_s_timed_region": wall, "loss_last": last,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4", choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=1024, help="samples per GPU per step")
+    ap.add_argument("--ref-batch", type=int, default=64, help="samples per CPU reference step (bounded sample)")
+    ap.add_argument("--dropout", type=float, default=0.0)
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

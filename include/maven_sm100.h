@@ -45,6 +45,13 @@ extern "C" {
 const char* mvn_last_error(void);
 int         mvn_abi_version(void);
 int         mvn_num_sms(void);   /* SM count of the current device (148 on B200) */
+long long   mvn_launch_count(void);   /* kernels this process has enqueued through the library */
+/* Per-kernel-class device timing for the roofline leg of bench.py: while a class bit is set, every launch of
+ * that class is bracketed by CUDA events on its own stream; mvn_prof_read sums and clears them.
+ * classes: 0 GEMM (fwd + input-grad), 1 weight-grad GEMM, 2 attention fwd, 3 attention bwd, 4 row kernels
+ * (embed/LN-bwd/pool/reduce), 5 CLIP loss, 6 optimizer, 7 ConvMixer. */
+void        mvn_prof_enable(unsigned class_mask);
+int         mvn_prof_read(int cls, double* total_ms, long long* count);
 
 /* ------------------------------------------------------------------------------------------------
  * Ragged packing.  Replaces the implicit "compute every padded position" of the reference and its

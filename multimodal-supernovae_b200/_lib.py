@@ -30,6 +30,9 @@ _SIGS = {
     "mvn_last_error": (c_char_p, []),
     "mvn_abi_version": (c_int, []),
     "mvn_num_sms": (c_int, []),
+    "mvn_launch_count": (ctypes.c_longlong, []),
+    "mvn_prof_enable": (None, [ctypes.c_uint]),
+    "mvn_prof_read": (c_int, [c_int, POINTER(c_double), POINTER(ctypes.c_longlong)]),
     "mvn_pack_plan": (c_int, [P, c_int, c_int, c_int, P, P, P, P]),
     "mvn_embed_fwd": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P]),
     "mvn_embed_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, c_size_t, P]),

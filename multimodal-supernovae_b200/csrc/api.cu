@@ -1,6 +1,8 @@
 // Error channel and device queries of the C ABI.
 #include <stdarg.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace mvn {
@@ -20,7 +22,46 @@ int num_sms() {
     }
     return cached;
 }
+static long long g_launches = 0;
+void note_launch() { ++g_launches; }
+
+static unsigned g_prof_mask = 0;
+struct ProfRec { cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof[PROF_NCLASS];
+static std::vector<cudaEvent_t> g_pool;
+static cudaEvent_t take_event() {
+    if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+ProfScope::ProfScope(int cls_, cudaStream_t st_) : cls(cls_), st(st_), stop(nullptr), on(false) {
+    if (g_prof_mask & (1u << cls)) {
+        on = true;
+        cudaEvent_t a = take_event();
+        stop = take_event();
+        cudaEventRecord(a, st);
+        g_prof[cls].push_back({a, stop});
+    }
+}
+ProfScope::~ProfScope() { if (on) cudaEventRecord(stop, st); }
 }  // namespace mvn
+
+extern "C" void mvn_prof_enable(unsigned class_mask) { mvn::g_prof_mask = class_mask; }
+extern "C" int mvn_prof_read(int cls, double* total_ms, long long* count) {
+    using namespace mvn;
+    if (cls < 0 || cls >= PROF_NCLASS || !total_ms || !count) { set_error("prof_read: bad arguments"); return MVN_E_BADARG; }
+    double ms = 0.0;
+    for (auto& r : g_prof[cls]) {
+        cudaEventSynchronize(r.b);
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.a, r.b);
+        ms += t;
+        g_pool.push_back(r.a); g_pool.push_back(r.b);
+    }
+    *total_ms = ms; *count = (long long)g_prof[cls].size();
+    g_prof[cls].clear();
+    return 0;
+}
+extern "C" long long mvn_launch_count(void) { return mvn::g_launches; }
 
 extern "C" const char* mvn_last_error(void) { return mvn::g_err; }
 extern "C" int mvn_abi_version(void) { return 1; }

@@ -248,6 +248,7 @@ extern "C" int mvn_attention_fwd(const float* qkv, const int32_t* cu_seqlens, co
     MVN_CHECK_ARG(aligned16(qkv) && aligned16(out), "attention_fwd: buffers must be 16-byte aligned");
     const int hd = E / H;
     cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(PROF_ATTN_FWD, st);
     const int grid = B * H;
     switch (hd) {
         case 4: attn_fwd_kernel<4><<<grid, ATT_THREADS, 0, st>>>(qkv, cu_seqlens, keyvalid, out, lse, E, H, scale); break;
@@ -268,6 +269,7 @@ extern "C" int mvn_attention_bwd(const float* qkv, const int32_t* cu_seqlens, co
     MVN_CHECK_ARG(aligned16(qkv) && aligned16(dout) && aligned16(dqkv), "attention_bwd: buffers must be 16-byte aligned");
     const int hd = E / H;
     cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(PROF_ATTN_BWD, st);
     const int grid = B * H;
     switch (hd) {
         case 4: attn_bwd_kernel<4><<<grid, ATT_THREADS, 0, st>>>(qkv, cu_seqlens, keyvalid, out, lse, dout, dqkv, E, H, scale); break;

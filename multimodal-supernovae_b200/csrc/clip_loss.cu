@@ -278,6 +278,7 @@ extern "C" int mvn_clip_loss_fwd(const float* e1_local, const float* e2_local, c
     MVN_TRY(check_loss_args(e1_local, e2_local, e1_all, e2_all, n, N, D, row_offset, logit_scale, logit_bias, workspace, workspace_bytes));
     MVN_CHECK_ARG(loss_out && lse_row && lse_col, "clip_loss_fwd: null outputs");
     cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(PROF_LOSS, st);
     const Split sp = make_split(n, N);
     float* ws = (float*)workspace;
     float* pm_r = ws;                       float* pl_r = pm_r + (size_t)sp.nsplit * n;
@@ -305,6 +306,7 @@ extern "C" int mvn_clip_loss_bwd(const float* e1_local, const float* e2_local, c
     MVN_TRY(check_loss_args(e1_local, e2_local, e1_all, e2_all, n, N, D, row_offset, logit_scale, logit_bias, workspace, workspace_bytes));
     MVN_CHECK_ARG(lse_row_all && lse_col_all && d_e1_local && d_e2_local && d_logit_scale, "clip_loss_bwd: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(PROF_LOSS, st);
     const Split sp = make_split(n, N);
     float* ws = (float*)workspace;
     float* part2 = ws;                                        // d_e2 partials  [nsplit][n][D]

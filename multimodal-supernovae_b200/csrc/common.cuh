@@ -39,6 +39,7 @@ void set_error(const char* fmt, ...);
 
 #define MVN_LAUNCH_CHECK()                                                          \
     do {                                                                            \
+        mvn::note_launch();                                                         \
         cudaError_t _e = cudaGetLastError();                                        \
         if (_e != cudaSuccess) {                                                    \
             mvn::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
@@ -57,6 +58,15 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int num_sms();
+void note_launch();
+
+// per-kernel-class device timing (bench.py's roofline leg): CUDA events on the launching stream
+enum ProfClass { PROF_GEMM = 0, PROF_WGRAD = 1, PROF_ATTN_FWD = 2, PROF_ATTN_BWD = 3, PROF_ROW = 4, PROF_LOSS = 5, PROF_OPTIM = 6, PROF_CONV = 7, PROF_NCLASS = 8 };
+struct ProfScope {
+    int cls; cudaStream_t st; cudaEvent_t stop; bool on;
+    ProfScope(int cls_, cudaStream_t st_);
+    ~ProfScope();
+};
 
 // number of row-slabs every weight-gradient style reduction is split into (partials are [kSlabs][...])
 constexpr int kSlabs = 128;

@@ -244,6 +244,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
 int launch_gemm(const float* A, const float* Bm, float* C, const int32_t* n_rows_dev, int M_cap, int N, int K,
                 bool b_is_nk, const GemmEpilogue& ep, int prec, cudaStream_t st) {
     MVN_CHECK_ARG(A && Bm && C && M_cap > 0 && N > 0 && K > 0, "gemm: null pointer or non-positive size (M=%d N=%d K=%d)", M_cap, N, K);
+    ProfScope prof(PROF_GEMM, st);
     if (prec == 1) {
         int r = launch_gemm_tc(A, Bm, C, n_rows_dev, M_cap, N, K, b_is_nk, ep, st);
         if (r != MVN_E_UNSUPPORTED) return r;     // shapes the tensor-core kernel does not cover use the FFMA kernel
@@ -275,6 +276,7 @@ int launch_wgrad_partials(const float* dY, const float* X, const int32_t* n_rows
                           float* partial, size_t pstride, size_t woff, long long boff, int prec, cudaStream_t st) {
     (void)prec;
     MVN_CHECK_ARG(dY && X && partial && M_cap > 0 && N > 0 && K > 0, "wgrad: null pointer or non-positive size");
+    ProfScope prof(PROF_WGRAD, st);
     dim3 grid(kSlabs, cdiv(N, 64), cdiv(K, 64));
     wgrad_kernel<<<grid, 256, 0, st>>>(dY, X, n_rows_dev, M_cap, N, K, partial, pstride, woff, boff,
                                        (N % 4 == 0) && aligned16(dY), (K % 4 == 0) && aligned16(X));
@@ -284,6 +286,7 @@ int launch_wgrad_partials(const float* dY, const float* X, const int32_t* n_rows
 
 int launch_reduce_partials(const float* partial, size_t pstride, size_t n, float* out, int accumulate, cudaStream_t st) {
     if (n == 0) return 0;
+    ProfScope prof(PROF_ROW, st);
     const int blocks = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
     reduce_partials_kernel<<<blocks, 256, 0, st>>>(partial, pstride, n, kSlabs, out, accumulate);
     MVN_LAUNCH_CHECK();

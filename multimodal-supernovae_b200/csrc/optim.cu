@@ -121,6 +121,7 @@ extern "C" int mvn_radam_step(float* param, const float* grad, float* exp_avg, f
                               float beta2, float eps, float weight_decay, float bias_correction1, float sqrt_bias_correction2, float rect,
                               void* stream) {
     MVN_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0, "radam_step: bad arguments");
+    ProfScope prof(PROF_OPTIM, (cudaStream_t)stream);
     const long long blocks = (n + 255) / 256;
     radam_kernel<<<(int)(blocks < 2368 ? blocks : 2368), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                                                        weight_decay, bias_correction1, sqrt_bias_correction2, rect);

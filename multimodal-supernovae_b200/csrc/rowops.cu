@@ -319,6 +319,7 @@ int launch_ln_bwd(const float* dY, const float* xhat, const float* rstd, const f
                   cudaStream_t st) {
     MVN_CHECK_ARG(dY && xhat && rstd && gamma && dZ && partial, "layernorm_bwd: null pointer");
     MVN_UNSUPPORTED(E >= 1 && E <= 128, "layernorm_bwd: E=%d outside [1,128]", E);
+    ProfScope prof(PROF_ROW, st);
     const int per = (E + 31) / 32;
     switch (per) {
         case 1: ln_bwd_kernel<1><<<kSlabs, 256, 0, st>>>(dY, xhat, rstd, gamma, dZ, n_rows_dev, M_cap, E, partial, pstride, goff, boff); break;
@@ -333,6 +334,7 @@ int launch_embed_bwd_partials(const float* x, const int32_t* tok_src, const floa
                               int M_cap, int T, int E, int nband, float* partial, size_t pstride, size_t off, cudaStream_t st) {
     MVN_CHECK_ARG(x && tok_src && dout && partial, "embed_bwd: null pointer");
     MVN_UNSUPPORTED(E >= 1 && E <= 128 && nband >= 1 && nband <= 4, "embed_bwd: E=%d nband=%d unsupported", E, nband);
+    ProfScope prof(PROF_ROW, st);
     const int per = (E + 31) / 32;
     switch (per) {
         case 1: embed_bwd_kernel<1><<<kSlabs, 256, 0, st>>>(x, tok_src, dout, n_rows_dev, M_cap, T, E, nband, partial, pstride, off); break;
@@ -352,6 +354,7 @@ extern "C" int mvn_pack_plan(const uint8_t* mask, int B, int T, int valid_only, 
     MVN_CHECK_ARG(B > 0 && T > 0 && cu_seqlens && tok_src && keyvalid, "pack_plan: bad arguments");
     MVN_CHECK_ARG((long long)B * T < (1ll << 31), "pack_plan: B*T overflows int32");
     cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(PROF_ROW, st);
     // counts are staged in tok_src[0..B) (B <= B*T), consumed by the scan before the index pass overwrites them
     int32_t* counts = tok_src;
     count_valid_kernel<<<cdiv(B * 32, 256), 256, 0, st>>>(mask, B, T, valid_only, counts);
@@ -372,6 +375,7 @@ extern "C" int mvn_embed_fwd(const float* x, const float* t, const int32_t* cu_s
     MVN_CHECK_ARG(E % 2 == 0, "embed_fwd: E must be even (sin/cos pairs), got %d", E);
     MVN_CHECK_ARG(nband >= 1 && (nband == 1 || (band_emb && T % nband == 0)), "embed_fwd: nband=%d needs band_emb and T%%nband==0", nband);
     const int blocks = min(cdiv(B * T, 8), num_sms() * 8);
+    ProfScope prof(PROF_ROW, (cudaStream_t)stream);
     embed_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, t, cu_seqlens, tok_src, div_term, w, b, band_emb, B, T, E, nband, out);
     MVN_LAUNCH_CHECK();
     return 0;
@@ -410,6 +414,7 @@ extern "C" int mvn_pool_fwd(const float* X, const int32_t* cu_seqlens, const uin
                             float* pooled, int32_t* argmax, void* stream) {
     MVN_CHECK_ARG(X && cu_seqlens && pooled && B > 0 && E > 0, "pool_fwd: bad arguments");
     MVN_CHECK_ARG(agg == MVN_AGG_MEAN || (agg == MVN_AGG_MAX && argmax), "pool_fwd: agg=%d unsupported or argmax missing", agg);
+    ProfScope prof(PROF_ROW, (cudaStream_t)stream);
     pool_fwd_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(X, cu_seqlens, keyvalid, T, E, agg, pooled, argmax);
     MVN_LAUNCH_CHECK();
     return 0;
@@ -420,6 +425,7 @@ extern "C" int mvn_pool_bwd(const float* dpooled, const int32_t* cu_seqlens, con
     (void)T;
     MVN_CHECK_ARG(dpooled && cu_seqlens && dX && B > 0 && E > 0, "pool_bwd: bad arguments");
     MVN_CHECK_ARG(agg == MVN_AGG_MEAN || (agg == MVN_AGG_MAX && argmax), "pool_bwd: agg=%d unsupported or argmax missing", agg);
+    ProfScope prof(PROF_ROW, (cudaStream_t)stream);
     pool_bwd_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(dpooled, cu_seqlens, keyvalid, argmax, E, agg, dX);
     MVN_LAUNCH_CHECK();
     return 0;

@@ -186,6 +186,29 @@ class LightCurveImageCLIP(_Base):
         self._segments = seg
         return g
 
+    def gather_grads(self) -> torch.Tensor:
+        """One flat gradient buffer for the whole model: gradients written by the fused ops already live in it; the few
+        produced by per-op functions (logit_scale, heads) are staged into their slots and `p.grad` is re-pointed at the
+        slot.  Used by FusedRAdam and by the data-parallel all-reduce (one NCCL call over the returned tensor)."""
+        g = self.flat_group()
+        flat = g.ensure()
+        gbuf = self._gbuf
+        if gbuf is None or gbuf.numel() != g.total or gbuf.device != flat.device:
+            gbuf = torch.zeros_like(flat)
+            self._gbuf = gbuf
+        gbase = gbuf.data_ptr()
+        with torch.no_grad():
+            for k, p in enumerate(g.params):
+                gr = p.grad
+                if gr is None:
+                    continue
+                o = g.offsets[k]
+                if gr.data_ptr() != gbase + 4 * o:
+                    v = gbuf[o:o + g.sizes[k]].view(p.shape)
+                    v.copy_(gr)
+                    p.grad = v
+        return gbuf
+
     def _new_gbuf(self, g: ops.FlatParams, device):
         if torch.is_grad_enabled():
             self._gbuf = torch.empty(g.total, dtype=torch.float32, device=device)

@@ -44,10 +44,7 @@ class FusedRAdam(torch.optim.Optimizer):
         g: ops.FlatParams = self.model.flat_group()
         flat = g.ensure()
         self._ensure_state(g, flat)
-        gbuf = getattr(self.model, "_gbuf", None)
-        if gbuf is None or gbuf.numel() != g.total:
-            gbuf = torch.empty_like(flat)
-        gbase = gbuf.data_ptr()
+        gbuf = self.model.gather_grads()
         in_group = {id(p) for p in grp["params"]}
         # contiguous runs of parameters that (a) have a gradient, (b) share the same step count
         runs = []
@@ -55,8 +52,6 @@ class FusedRAdam(torch.optim.Optimizer):
             if p.grad is None or id(p) not in in_group:
                 continue
             o, n = g.offsets[k], g.sizes[k]
-            if p.grad.data_ptr() != gbase + 4 * o:          # gradient produced outside the fused ops: stage it
-                gbuf[o:o + n].view(p.shape).copy_(p.grad)
             self._steps[k] += 1
             st = self._steps[k]
             if runs and runs[-1][1] == o and runs[-1][2] == st:
