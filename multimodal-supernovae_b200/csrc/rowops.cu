@@ -161,36 +161,54 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict_
 
 // ---------------------------------------------------------------------------------------------------
 // LayerNorm backward: dz = rstd * (g - mean(g) - xhat*mean(g*xhat)), g = dy*gamma; partial dgamma/dbeta per CTA
+constexpr int LNB_WARPS = 32;      // 1024-thread CTAs: one CTA per slab keeps the partial layout, 32 warps keep HBM busy
 template <int PER>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ xhat,
-                                                     const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                                     float* __restrict__ dZ, const int32_t* n_rows_dev, int M_cap, int E,
-                                                     float* __restrict__ partial, size_t pstride, size_t goff, size_t boff) {
-    __shared__ float red[8][2 * 32 * PER];
+__global__ void __launch_bounds__(LNB_WARPS * 32) ln_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ xhat,
+                                                                const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                                float* __restrict__ dZ, const int32_t* n_rows_dev, int M_cap, int E,
+                                                                float* __restrict__ partial, size_t pstride, size_t goff, size_t boff) {
+    __shared__ float red[LNB_WARPS][2 * 32 * PER];
     const int rows = n_rows_dev ? min(*n_rows_dev, M_cap) : M_cap;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float gam[PER], dg[PER], dbt[PER];
 #pragma unroll
     for (int p = 0; p < PER; ++p) { const int e = lane + 32 * p; gam[p] = e < E ? gamma[e] : 0.f; dg[p] = 0.f; dbt[p] = 0.f; }
     const float invE = 1.0f / (float)E;
-    for (int m = blockIdx.x * 8 + wid; m < rows; m += gridDim.x * 8) {
-        float dy[PER], xh[PER], s1 = 0.f, s2 = 0.f;
+    const int stride = gridDim.x * LNB_WARPS;
+    for (int m0 = blockIdx.x * LNB_WARPS + wid; m0 < rows; m0 += 2 * stride) {
+        // two rows in flight per warp (independent loads issued before either reduction)
+        float dy[2][PER], xh[2][PER], rs[2];
 #pragma unroll
-        for (int p = 0; p < PER; ++p) {
-            const int e = lane + 32 * p;
-            dy[p] = e < E ? dY[(size_t)m * E + e] : 0.f;
-            xh[p] = e < E ? xhat[(size_t)m * E + e] : 0.f;
-            const float g = dy[p] * gam[p];
-            s1 += g; s2 = fmaf(g, xh[p], s2);
-            dg[p] = fmaf(dy[p], xh[p], dg[p]);
-            dbt[p] += dy[p];
+        for (int u = 0; u < 2; ++u) {
+            const int m = m0 + u * stride;
+            const bool live = m < rows;
+            rs[u] = live ? rstd[m] : 0.f;
+#pragma unroll
+            for (int p = 0; p < PER; ++p) {
+                const int e = lane + 32 * p;
+                dy[u][p] = (live && e < E) ? dY[(size_t)m * E + e] : 0.f;
+                xh[u][p] = (live && e < E) ? xhat[(size_t)m * E + e] : 0.f;
+            }
         }
-        s1 = warp_sum(s1) * invE; s2 = warp_sum(s2) * invE;
-        const float rs = rstd[m];
 #pragma unroll
-        for (int p = 0; p < PER; ++p) {
-            const int e = lane + 32 * p;
-            if (e < E) dZ[(size_t)m * E + e] = rs * (dy[p] * gam[p] - s1 - xh[p] * s2);
+        for (int u = 0; u < 2; ++u) {
+            const int m = m0 + u * stride;
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int p = 0; p < PER; ++p) {
+                const float g = dy[u][p] * gam[p];
+                s1 += g; s2 = fmaf(g, xh[u][p], s2);
+                dg[p] = fmaf(dy[u][p], xh[u][p], dg[p]);
+                dbt[p] += dy[u][p];
+            }
+            s1 = warp_sum(s1) * invE; s2 = warp_sum(s2) * invE;
+            if (m < rows) {
+#pragma unroll
+                for (int p = 0; p < PER; ++p) {
+                    const int e = lane + 32 * p;
+                    if (e < E) dZ[(size_t)m * E + e] = rs[u] * (dy[u][p] * gam[p] - s1 - xh[u][p] * s2);
+                }
+            }
         }
     }
 #pragma unroll
@@ -202,7 +220,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
         if (e >= E) continue;
         float s = 0.f;
 #pragma unroll
-        for (int w8 = 0; w8 < 8; ++w8) s += red[w8][i];
+        for (int w8 = 0; w8 < LNB_WARPS; ++w8) s += red[w8][i];
         pp[(sec == 0 ? goff : boff) + e] = s;
     }
 }
@@ -322,9 +340,9 @@ int launch_ln_bwd(const float* dY, const float* xhat, const float* rstd, const f
     ProfScope prof(PROF_ROW, st);
     const int per = (E + 31) / 32;
     switch (per) {
-        case 1: ln_bwd_kernel<1><<<kSlabs, 256, 0, st>>>(dY, xhat, rstd, gamma, dZ, n_rows_dev, M_cap, E, partial, pstride, goff, boff); break;
-        case 2: ln_bwd_kernel<2><<<kSlabs, 256, 0, st>>>(dY, xhat, rstd, gamma, dZ, n_rows_dev, M_cap, E, partial, pstride, goff, boff); break;
-        default: ln_bwd_kernel<4><<<kSlabs, 256, 0, st>>>(dY, xhat, rstd, gamma, dZ, n_rows_dev, M_cap, E, partial, pstride, goff, boff); break;
+        case 1: ln_bwd_kernel<1><<<kSlabs, LNB_WARPS * 32, 0, st>>>(dY, xhat, rstd, gamma, dZ, n_rows_dev, M_cap, E, partial, pstride, goff, boff); break;
+        case 2: ln_bwd_kernel<2><<<kSlabs, LNB_WARPS * 32, 0, st>>>(dY, xhat, rstd, gamma, dZ, n_rows_dev, M_cap, E, partial, pstride, goff, boff); break;
+        default: ln_bwd_kernel<4><<<kSlabs, LNB_WARPS * 32, 0, st>>>(dY, xhat, rstd, gamma, dZ, n_rows_dev, M_cap, E, partial, pstride, goff, boff); break;
     }
     MVN_LAUNCH_CHECK();
     return 0;

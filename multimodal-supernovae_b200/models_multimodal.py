@@ -61,6 +61,24 @@ class ConvMixer(nn.Module):
             out += [self.net[3 + d][0].fn[2], self.net[3 + d][3]]
         return out
 
+    def running_flat(self, device) -> torch.Tensor:
+        """BatchNorm running_mean/var of every BN as views of one [nbn, 2, dim] buffer (state_dict names unchanged)."""
+        bns = self.bn_layers()
+        flat = getattr(self, "_running", None)
+        ok = flat is not None and flat.device == device
+        if ok:
+            base = flat.data_ptr()
+            ok = all(bn.running_mean.data_ptr() == base + 4 * (2 * i) * self.dim and bn.running_var.data_ptr() == base + 4 * (2 * i + 1) * self.dim
+                     for i, bn in enumerate(bns))
+        if not ok:
+            flat = torch.empty(len(bns), 2, self.dim, dtype=torch.float32, device=device)
+            for i, bn in enumerate(bns):
+                flat[i, 0].copy_(bn.running_mean); flat[i, 1].copy_(bn.running_var)
+                bn._buffers["running_mean"] = flat[i, 0]
+                bn._buffers["running_var"] = flat[i, 1]
+            self._running = flat
+        return flat
+
     def core_params(self):
         ps = [self.net[0].weight, self.net[2].weight, self.net[2].bias]
         for d in range(self.depth):

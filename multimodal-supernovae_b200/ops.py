@@ -423,9 +423,87 @@ class ConvCall:
 
 
 class ConvMixerFn(torch.autograd.Function):
+    """mvn_convmixer_fwd_stage / _bwd_stage, one stage per BatchNorm.  Under a data-parallel group the per-channel
+    batch sums are all-reduced between stages (SyncBN semantics: statistics of the GLOBAL batch)."""
+
     @staticmethod
-    def forward(ctx, x, call, *params):
-        raise NotImplementedError("maven_b200: ConvMixer kernels are not built yet")
+    def forward(ctx, x, call: ConvCall, *params):
+        from ._lib import ConvCfg
+        L = lib()
+        x = _req(x, "x_img")
+        if x.dim() != 4:
+            raise ValueError(f"ConvMixer expects (B, C, H, W), got {tuple(x.shape)}")
+        m = call.module
+        B, C, H, W = x.shape
+        if C != m.channels:
+            raise ValueError(f"ConvMixer built for {m.channels} channels, got {C}")
+        grp = _DP_GROUP if m.training else None
+        world = 1
+        if grp is not None:
+            import torch.distributed as dist
+            world = dist.get_world_size(grp)
+        P = (H // m.patch_size) * (W // m.patch_size)
+        bn0 = m.net[2]
+        cfg = ConvCfg(B=B, C=C, H=H, W=W, dim=m.dim, depth=m.depth, kernel_size=m.kernel_size, patch_size=m.patch_size, n_out=m.n_out,
+                      enc_dim=call.enc_dim, hidden=m.projection[2].out_features, normalize=1 if call.normalize else 0,
+                      training=1 if m.training else 0, prec=call.prec, bn_eps=bn0.eps, bn_momentum=bn0.momentum if bn0.momentum is not None else 0.1,
+                      global_count=B * P * world)
+        need = L.mvn_conv_param_count(ctypes.byref(cfg))
+        if need != call.count:
+            raise RuntimeError(f"maven_b200: ConvMixer parameter layout mismatch (library {need}, module {call.count}): "
+                               + L.mvn_last_error().decode())
+        nbn = 1 + 2 * m.depth
+        wsb = L.mvn_conv_workspace_bytes(ctypes.byref(cfg))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
+        stats = torch.zeros(nbn, 2 * m.dim, dtype=torch.float64, device=x.device)
+        running = m.running_flat(x.device)
+        D = call.enc_dim if call.enc_dim > 0 else m.n_out
+        out = torch.empty(B, D, dtype=torch.float32, device=x.device)
+        pview = call.flat[call.off:call.off + call.count]
+        for s in range(nbn + 1):
+            check(L.mvn_convmixer_fwd_stage(ctypes.byref(cfg), s, _p(pview), _p(x), _p(running), _p(stats), _p(out), _p(ws), wsb, _stream()),
+                  "convmixer_fwd_stage")
+            if world > 1 and s < nbn:
+                import torch.distributed as dist
+                dist.all_reduce(stats[s], group=grp)
+        _count(5 + 6 * m.depth * 2 + 8)
+        if m.training:
+            torch._foreach_add_([bn.num_batches_tracked for bn in m.bn_layers()], 1)
+        ctx.cfg, ctx.ws, ctx.stats, ctx.x, ctx.pview, ctx.call, ctx.world, ctx.grp = cfg, ws, stats, x, pview, call, world, grp
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = lib()
+        dout = _req(dout, "grad_output")
+        call: ConvCall = ctx.call
+        cfg = ctx.cfg
+        nbn = 1 + 2 * cfg.depth
+        if call.gbuf is not None:
+            g = call.gbuf[call.goff:call.goff + call.count]
+        else:
+            g = torch.empty(call.count, dtype=torch.float32, device=dout.device)
+        sb = torch.zeros(nbn, 2 * cfg.dim, dtype=torch.float64, device=dout.device)
+        for s in range(nbn, -1, -1):
+            check(L.mvn_convmixer_bwd_stage(ctypes.byref(cfg), s, _p(ctx.pview), _p(ctx.x), _p(ctx.stats), _p(sb), _p(dout), _p(g), _p(ctx.ws),
+                                            ctx.ws.numel(), _stream()), "convmixer_bwd_stage")
+            if ctx.world > 1 and s > 0:
+                import torch.distributed as dist
+                dist.all_reduce(sb[s - 1], group=ctx.grp)
+        _count(10 + 8 * cfg.depth * 2)
+        needs = ctx.needs_input_grad[2:]
+        grp: FlatParams = call.group
+        i0, i1 = call.pidx
+        base = grp.offsets[i0]
+        grads = []
+        for k, need in zip(range(i0, i1), needs):
+            if need:
+                o = grp.offsets[k] - base
+                grads.append(g[o:o + grp.sizes[k]].view(grp.params[k].shape))
+            else:
+                grads.append(None)
+        ctx.ws = None
+        return (None, None) + tuple(grads)
 
 
 class QueryPoolFn(torch.autograd.Function):

@@ -297,6 +297,7 @@ MODEL_CFG = dict(
     conv_kwargs=dict(dim=32, depth=2, channels=3, kernel_size=5, patch_size=10, n_out=32, dropout_prob=0.0),
 )
 MODEL_CASES = {
+    "model_clip3": dict(combinations=["lightcurve", "spectral", "host_galaxy"]),
     "model_clip2": dict(combinations=["lightcurve", "spectral"]),
     "model_cls5": dict(combinations=["lightcurve"], classification=True, n_classes=5),
     "model_reg": dict(combinations=["lightcurve"], regression=True),
@@ -338,6 +339,41 @@ def test_training_step_golden(name):
     outs = out if isinstance(out, list) else [out]
     for i, o in enumerate(outs):
         assert relerr(o, g[f"eval_out{i}"]) < TOL
+
+
+def test_convmixer_golden():
+    """A8: train-mode forward, parameter grads, running-stat update, then eval-mode forward."""
+    from maven_b200.models_multimodal import ConvMixer
+    g = load_golden("convmixer")
+    cm = ConvMixer(dim=32, depth=2, channels=3, kernel_size=5, patch_size=10, n_out=32, dropout_prob=0.0)
+    sd, grads, after = split_golden(g)
+    cm.load_state_dict(sd)
+    cm = cm.to(dev()).train()
+    y = cm(g["img"].to(dev()))
+    assert relerr(y, g["y"]) < 2 * TOL
+    (y * g["w"].to(dev())).sum().backward()
+    for k, p in cm.named_parameters():
+        assert relerr(p.grad, grads[k]) < GTOL or (p.grad.cpu() - grads[k]).abs().max() < 1e-6, k
+    now = cm.state_dict()
+    for k, ref in after.items():
+        if "num_batches" in k:
+            assert int(now[k]) == int(ref), k
+        else:
+            assert relerr(now[k], ref) < TOL, k
+    cm.eval()
+    with torch.no_grad():
+        assert relerr(cm(g["img"].to(dev())), g["y_eval"]) < 2 * TOL
+
+
+def test_convmixer_vs_oracle_batch():
+    from maven_b200.models_multimodal import ConvMixer
+    torch.manual_seed(11)
+    cm = ConvMixer(dim=32, depth=2, channels=3, kernel_size=5, patch_size=10, n_out=32, dropout_prob=0.0)
+    sd = {k: v.detach().clone() for k, v in cm.state_dict().items()}
+    img = torch.rand(130, 3, 60, 60)
+    ref = O.convmixer({k: v.double() for k, v in sd.items()}, "", img.double(), depth=2, kernel_size=5, patch_size=10, training=True)
+    y = cm.to(dev()).train()(img.to(dev()))
+    assert relerr(y, ref) < 2 * TOL
 
 
 def test_radam_trajectory_golden(L):

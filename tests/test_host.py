@@ -55,6 +55,17 @@ def test_seq_param_layout_matches_library(built, kw):
     assert all(n.startswith(("projection", "query", "agg_attn")) for n in rest), rest
 
 
+def test_conv_param_layout_matches_library(built):
+    from maven_b200.models_multimodal import ConvMixer
+    cm = ConvMixer(dim=32, depth=2, channels=3, kernel_size=5, patch_size=10, n_out=32, dropout_prob=0.0)
+    cfg = built.ConvCfg(B=4, C=3, H=60, W=60, dim=32, depth=2, kernel_size=5, patch_size=10, n_out=32, enc_dim=0, hidden=1024,
+                        normalize=0, training=1, prec=0, bn_eps=1e-5, bn_momentum=0.1, global_count=4 * 36)
+    assert built.lib().mvn_conv_param_count(ctypes.byref(cfg)) == sum(p.numel() for p in cm.core_params()) == sum(p.numel() for p in cm.parameters())
+    assert built.lib().mvn_conv_num_bn(ctypes.byref(cfg)) == len(cm.bn_layers()) == 5
+    cfg.enc_dim = 128
+    assert built.lib().mvn_conv_param_count(ctypes.byref(cfg)) == sum(p.numel() for p in cm.parameters()) + 128 * 32 + 128
+
+
 def test_state_dict_keys_match_reference_contract():
     """names/shapes the shipped checkpoints carry (checked against a committed golden)."""
     from conftest import load_golden
