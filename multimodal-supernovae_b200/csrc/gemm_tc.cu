@@ -1,8 +1,398 @@
-// tcgen05 / TMEM / TMA tensor-core GEMM (prec==1).  Placeholder until the kernel lands: reports "unsupported" so
-// launch_gemm falls through to the FFMA kernel.
-#include "common.cuh"
+// Tensor-core tier (prec==1) of the token-stream GEMMs:  C[M,N] = A[M,K] * op(B)  with the fused epilogues of
+// gemm_simt.cu (bias / ReLU / residual / ReLU-mask / residual+LayerNorm).
+//
+// Shape of the problem: M = packed tokens (1e5..1e6), K and N in {32..256}.  The weight matrix is tiny and the
+// activation stream is read once and written once, so the kernel is HBM-bound by construction; the design goal is to
+// keep the memory system saturated while the contraction itself rides on tcgen05:
+//   * persistent CTAs (one per SM), static round-robin over 128-row tiles;
+//   * warp 0: TMA producer -- fp32 A tiles, [128 rows x 32 floats] boxes with the 128-byte swizzle, into an
+//     8-deep ring of 16 KB stages (128 KB of loads in flight per SM);
+//   * warp 1: allocates TMEM, then one thread issues tcgen05.mma kind::tf32 (M=128, N=N, K=8 per instruction;
+//     fp32 bit patterns are consumed directly, so there is no conversion pass) into one of two TMEM accumulators;
+//   * the weight matrix is staged once per CTA in the same swizzled K-major layout (transposed on the fly for
+//     input-gradient GEMMs, rounded to nearest TF32);
+//   * warps 2-5: epilogue -- tcgen05.ld gives every thread one output row (32 columns at a time), so LayerNorm
+//     statistics need no shuffles; tiles go through a small per-warp shared-memory transpose so that every global
+//     load/store of C, the residual, xhat ... is a full 128-byte line.
+#include <mutex>
+#include <unordered_map>
+
+#include "tc_common.cuh"
+
 namespace mvn {
-int launch_gemm_tc(const float*, const float*, float*, const int32_t*, int, int, int, bool, const GemmEpilogue&, cudaStream_t) {
-    return MVN_E_UNSUPPORTED;
+namespace tc {
+
+// ---- tensor-map cache ------------------------------------------------------------------------------------
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
 }
+struct Key {
+    const void* p; int rows, cols, box;
+    bool operator==(const Key& o) const { return p == o.p && rows == o.rows && cols == o.cols && box == o.box; }
+};
+struct KeyHash {
+    size_t operator()(const Key& k) const {
+        return std::hash<const void*>()(k.p) ^ ((size_t)k.rows * 0x9E3779B97F4A7C15ull) ^ ((size_t)k.cols << 40) ^ ((size_t)k.box << 52);
+    }
+};
+std::mutex g_mu;
+std::unordered_map<Key, CUtensorMap*, KeyHash> g_maps;
+}  // namespace
+
+const CUtensorMap* get_tmap_2d(const float* base, int rows, int cols, int box_rows) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    Key k{base, rows, cols, box_rows};
+    auto it = g_maps.find(k);
+    if (it != g_maps.end()) return it->second;
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return nullptr; }
+    if (g_maps.size() > 4096) {                    // pointers churn (caching allocator): keep the table bounded
+        for (auto& kv : g_maps) delete kv.second;
+        g_maps.clear();
+    }
+    CUtensorMap* m = new CUtensorMap;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+    cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for [%d x %d] box %d", (int)r, rows, cols, box_rows);
+        delete m;
+        return nullptr;
+    }
+    g_maps.emplace(k, m);
+    return m;
+}
+
+}  // namespace tc
+
+namespace {
+using namespace tc;
+
+constexpr int TILE_M = 128;
+constexpr int STAGE_BYTES = TILE_M * 128;        // one [128 x 32 fp32] K-chunk of A
+constexpr int NSTAGE = 8;
+constexpr int MAX_B_BYTES = 65536;               // N*K*4 <= 64 KB (256x64, 64x256, 192x64 ...)
+constexpr int STG_PITCH = 36;                    // floats; 16-B aligned rows, conflict-free for 128-bit accesses
+constexpr int STG_FLOATS = 32 * STG_PITCH;
+constexpr int NUM_EPI_WARPS = 4;
+constexpr int NTHREADS = 32 * (2 + NUM_EPI_WARPS);
+constexpr int TMEM_COLS = 512;
+
+// dynamic shared memory carve-up (byte offsets from the 1024-aligned base)
+constexpr int OFF_A = 0;
+constexpr int OFF_B = OFF_A + NSTAGE * STAGE_BYTES;                 // 131072
+constexpr int OFF_STG = OFF_B + MAX_B_BYTES;                        // 196608
+constexpr int OFF_VEC = OFF_STG + NUM_EPI_WARPS * STG_FLOATS * 4;   // bias[256] gamma[64] beta[64]
+constexpr int OFF_BAR = OFF_VEC + (256 + 64 + 64) * 4;
+constexpr int NUM_BARS = 2 * NSTAGE + 4;
+constexpr int OFF_TMEMPTR = OFF_BAR + NUM_BARS * 8;
+constexpr int SMEM_BYTES = OFF_TMEMPTR + 16 + 1024;                 // + slack for the manual 1024-B alignment
+
+struct TcArgs {
+    const float* B; float* C;
+    const int32_t* n_rows_dev;
+    int M_cap, N, K, b_is_nk;
+    GemmEpilogue ep;
+};
+
+// coalesced [32 rows x 32 cols] block of a row-major [*, ld] matrix -> staging (row pitch STG_PITCH)
+__device__ __forceinline__ void stage_load(float* stg, const float* __restrict__ src, int row0, int rows, int ld, int c0, int lane) {
+    const int cq = (lane & 7) * 4, rr = lane >> 3;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = rr + 4 * i;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row0 + r < rows) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)(row0 + r) * ld + c0 + cq));
+        *reinterpret_cast<float4*>(stg + r * STG_PITCH + cq) = v;
+    }
+}
+__device__ __forceinline__ void stage_store(const float* stg, float* __restrict__ dst, int row0, int rows, int ld, int c0, int lane) {
+    const int cq = (lane & 7) * 4, rr = lane >> 3;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = rr + 4 * i;
+        if (row0 + r < rows) *reinterpret_cast<float4*>(dst + (size_t)(row0 + r) * ld + c0 + cq) = *reinterpret_cast<const float4*>(stg + r * STG_PITCH + cq);
+    }
+}
+__device__ __forceinline__ void row_read(const float* stg, int lane, float* v) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(stg + lane * STG_PITCH + j);
+        v[j] = t.x; v[j + 1] = t.y; v[j + 2] = t.z; v[j + 3] = t.w;
+    }
+}
+__device__ __forceinline__ void row_write(float* stg, int lane, const float* v) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(stg + lane * STG_PITCH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+}
+
+// LN_CH: 0 = plain epilogue; 1 or 2 = residual+LayerNorm epilogue over N = 32*LN_CH columns.
+template <int LN_CH>
+__global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const TcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int N = a.N, K = a.K, KC = K >> 5;
+    const int rows = a.n_rows_dev ? min(*a.n_rows_dev, a.M_cap) : a.M_cap;
+    const int ntiles = (rows + TILE_M - 1) / TILE_M;
+
+    float* Bs = reinterpret_cast<float*>(smem + OFF_B);
+    float* vec = reinterpret_cast<float*>(smem + OFF_VEC);
+    const uint32_t bar0 = sbase + OFF_BAR;
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
+    auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * NSTAGE + b); };
+    auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * NSTAGE + 2 + b); };
+    volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEMPTR);
+
+    // ---- one-time setup ------------------------------------------------------------------------------
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmapA);
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), NUM_EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(sbase + OFF_TMEMPTR, TMEM_COLS);
+    // weights -> swizzled K-major smem: element (n,k) lives in block kc=k/32 at sw128_off(n, k%32); rounded to TF32
+    if (a.b_is_nk) {                 // B[n][k], k contiguous
+        for (int idx = threadIdx.x; idx < N * (K >> 2); idx += NTHREADS) {
+            const int n = idx / (K >> 2), k = (idx % (K >> 2)) << 2;
+            const float4 w = __ldg(reinterpret_cast<const float4*>(a.B + (size_t)n * K + k));
+            const float4 t = make_float4(to_tf32(w.x), to_tf32(w.y), to_tf32(w.z), to_tf32(w.w));
+            *reinterpret_cast<float4*>(Bs + (size_t)(k >> 5) * N * 32 + sw128_off(n, k & 31)) = t;
+        }
+    } else {                         // B[k][n], n contiguous: transpose while staging
+        for (int idx = threadIdx.x; idx < K * N; idx += NTHREADS) {
+            const int k = idx / N, n = idx % N;
+            Bs[(size_t)(k >> 5) * N * 32 + sw128_off(n, k & 31)] = to_tf32(__ldg(a.B + idx));
+        }
+    }
+    for (int i = threadIdx.x; i < N; i += NTHREADS) vec[i] = a.ep.bias ? a.ep.bias[i] : 0.f;
+    if (LN_CH > 0) {
+        for (int i = threadIdx.x; i < N; i += NTHREADS) { vec[256 + i] = a.ep.gamma[i]; vec[320 + i] = a.ep.beta[i]; }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int kc = 0; kc < KC; ++kc, ++it) {
+                    const int s = it % NSTAGE;
+                    mbar_wait(empty_bar(s), ((it / NSTAGE) & 1) ^ 1);
+                    mbar_expect_tx(full_bar(s), STAGE_BYTES);
+                    tma_load_2d(sbase + OFF_A + s * STAGE_BYTES, &tmapA, full_bar(s), kc * 32, tile * TILE_M);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = idesc_tf32(TILE_M, N, 0, 0);
+            uint32_t it = 0, tc_i = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tc_i) {
+                const int buf = tc_i & 1;
+                mbar_wait(tempty_bar(buf), ((tc_i >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * 256;
+                for (int kc = 0; kc < KC; ++kc, ++it) {
+                    const int s = it % NSTAGE;
+                    mbar_wait(full_bar(s), (it / NSTAGE) & 1);
+                    tc_fence_after();
+                    const uint32_t a_addr = sbase + OFF_A + s * STAGE_BYTES;
+                    const uint32_t b_addr = sbase + OFF_B + kc * N * 128;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        umma_tf32(d_tmem, smem_desc_sw128(a_addr + j * 32, 0, 1024), smem_desc_sw128(b_addr + j * 32, 0, 1024), idesc,
+                                  (kc | j) != 0);
+                    umma_commit(empty_bar(s));            // frees the A stage once these MMAs have read it
+                }
+                umma_commit(tfull_bar(buf));              // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ===== epilogue warps: TMEM lanes 32*(warp%4) .. +31 =====
+        const int quad = warp & 3;
+        float* stg = reinterpret_cast<float*>(smem + OFF_STG) + (warp - 2) * STG_FLOATS;
+        const GemmEpilogue& ep = a.ep;
+        uint32_t tc_i = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tc_i) {
+            const int buf = tc_i & 1;
+            mbar_wait(tfull_bar(buf), (tc_i >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + buf * 256 + ((uint32_t)(quad * 32) << 16);
+            const int row0 = tile * TILE_M + quad * 32;
+            if constexpr (LN_CH == 0) {
+                for (int c0 = 0; c0 < N; c0 += 32) {
+                    float v[32];
+                    const bool half = (N - c0) < 32;          // N % 32 == 16: last chunk has 16 columns
+                    if (half) {
+                        tmem_ld16(taddr + c0, v);
+#pragma unroll
+                        for (int j = 16; j < 32; ++j) v[j] = 0.f;
+                    } else {
+                        tmem_ld32(taddr + c0, v);
+                    }
+                    const int nc = half ? 16 : 32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += vec[(c0 + j) & 255];
+                    if (ep.addend) {
+                        float r[32];
+                        __syncwarp();
+                        if (!half) stage_load(stg, ep.addend, row0, rows, N, c0, lane);
+                        else if ((lane & 7) < 4) stage_load(stg, ep.addend, row0, rows, N, c0, lane);
+                        __syncwarp();
+                        row_read(stg, lane, r);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] += r[j];
+                    }
+                    if (ep.act == MVN_ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                    } else if (ep.act == MVN_ACT_GELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                    }
+                    if (ep.dact) {
+                        float r[32];
+                        __syncwarp();
+                        if (!half) stage_load(stg, ep.act_src, row0, rows, N, c0, lane);
+                        else if ((lane & 7) < 4) stage_load(stg, ep.act_src, row0, rows, N, c0, lane);
+                        __syncwarp();
+                        row_read(stg, lane, r);
+                        if (ep.dact == 1) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = r[j] > 0.f ? v[j] : 0.f;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_grad(r[j]);
+                        }
+                    }
+                    __syncwarp();
+                    row_write(stg, lane, v);
+                    __syncwarp();
+                    if (!half) stage_store(stg, a.C, row0, rows, N, c0, lane);
+                    else if ((lane & 7) < 4) stage_store(stg, a.C, row0, rows, N, c0, lane);
+                    (void)nc;
+                }
+            } else {
+                float v[LN_CH][32];
+#pragma unroll
+                for (int c = 0; c < LN_CH; ++c) {
+                    tmem_ld32(taddr + c * 32, v[c]);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[c][j] += vec[c * 32 + j];
+                    if (ep.addend) {
+                        float r[32];
+                        __syncwarp();
+                        stage_load(stg, ep.addend, row0, rows, N, c * 32, lane);
+                        __syncwarp();
+                        row_read(stg, lane, r);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[c][j] += r[j];
+                    }
+                }
+                float sum = 0.f;
+#pragma unroll
+                for (int c = 0; c < LN_CH; ++c)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sum += v[c][j];
+                const float invn = 1.0f / (float)(32 * LN_CH);
+                const float mean = sum * invn;
+                float sq = 0.f;
+#pragma unroll
+                for (int c = 0; c < LN_CH; ++c)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { v[c][j] -= mean; sq = fmaf(v[c][j], v[c][j], sq); }
+                const float rs = rsqrtf(sq * invn + ep.eps);
+                if (ep.rstd && row0 + lane < rows) ep.rstd[row0 + lane] = rs;
+#pragma unroll
+                for (int c = 0; c < LN_CH; ++c) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[c][j] *= rs;
+                    if (ep.xhat) {
+                        __syncwarp();
+                        row_write(stg, lane, v[c]);
+                        __syncwarp();
+                        stage_store(stg, ep.xhat, row0, rows, N, c * 32, lane);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[c][j] = fmaf(v[c][j], vec[256 + c * 32 + j], vec[320 + c * 32 + j]);
+                    __syncwarp();
+                    row_write(stg, lane, v[c]);
+                    __syncwarp();
+                    stage_store(stg, a.C, row0, rows, N, c * 32, lane);
+                }
+            }
+            // this warp has drained its TMEM lanes of accumulator `buf`
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(buf));
+        }
+    }
+
+    // ---- teardown ------------------------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int LN_CH>
+int launch_tc(const CUtensorMap& tm, const TcArgs& a, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        MVN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<LN_CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    const int tiles = cdiv(a.M_cap, TILE_M);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    tc_gemm_kernel<LN_CH><<<grid, NTHREADS, SMEM_BYTES, st>>>(tm, a);
+    MVN_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+int launch_gemm_tc(const float* A, const float* Bm, float* C, const int32_t* n_rows_dev, int M_cap, int N, int K, bool b_is_nk,
+                   const GemmEpilogue& ep, cudaStream_t st) {
+    // shapes this kernel is built for; anything else stays on the FFMA kernel
+    if (K % 32 != 0 || K > 256 || N % 16 != 0 || N < 16 || N > 256 || (size_t)N * K * 4 > (size_t)MAX_B_BYTES) return MVN_E_UNSUPPORTED;
+    if (M_cap < TILE_M) return MVN_E_UNSUPPORTED;          // tiny heads: not worth a persistent launch
+    const bool ln = ep.gamma != nullptr;
+    if (ln && !(N == 32 || N == 64)) return MVN_E_UNSUPPORTED;
+    if (!aligned16(A) || !aligned16(C) || !aligned16(Bm) || (ep.addend && !aligned16(ep.addend)) || (ep.act_src && !aligned16(ep.act_src)) ||
+        (ep.xhat && !aligned16(ep.xhat)))
+        return MVN_E_UNSUPPORTED;
+    if (ln) MVN_CHECK_ARG(ep.beta != nullptr, "gemm+LN: beta missing");
+    const CUtensorMap* tm = get_tmap_2d(A, M_cap, K, TILE_M);
+    if (!tm) return MVN_E_BADARG;
+    TcArgs a;
+    a.B = Bm; a.C = C; a.n_rows_dev = n_rows_dev; a.M_cap = M_cap; a.N = N; a.K = K; a.b_is_nk = b_is_nk ? 1 : 0; a.ep = ep;
+    if (!ln) return launch_tc<0>(*tm, a, st);
+    return N == 32 ? launch_tc<1>(*tm, a, st) : launch_tc<2>(*tm, a, st);
+}
+
 }  // namespace mvn
