@@ -239,16 +239,25 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const float* __re
 }  // namespace
 }  // namespace mvn
 
+namespace mvn {
+int launch_attention_fwd_tc(const float* qkv, const int32_t* cu, float* out, float* lse, int B, int E, int H, float scale, cudaStream_t st);
+int launch_attention_bwd_tc(const float* qkv, const int32_t* cu, const float* out, const float* lse, const float* dout, float* dqkv,
+                            int B, int E, int H, float scale, cudaStream_t st);
+}  // namespace mvn
+
 using namespace mvn;
 
 extern "C" int mvn_attention_fwd(const float* qkv, const int32_t* cu_seqlens, const uint8_t* keyvalid, float* out, float* lse,
                                  int B, int E, int H, float scale, int prec, void* stream) {
-    (void)prec;
     MVN_CHECK_ARG(qkv && cu_seqlens && out && lse && B > 0 && E > 0 && H > 0 && E % H == 0, "attention_fwd: bad arguments (E=%d H=%d)", E, H);
     MVN_CHECK_ARG(aligned16(qkv) && aligned16(out), "attention_fwd: buffers must be 16-byte aligned");
     const int hd = E / H;
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope prof(PROF_ATTN_FWD, st);
+    if (prec == 1 && keyvalid == nullptr) {       // packed stream, every key live: tensor-core kernel
+        const int r = launch_attention_fwd_tc(qkv, cu_seqlens, out, lse, B, E, H, scale, st);
+        if (r != MVN_E_UNSUPPORTED) return r;
+    }
     const int grid = B * H;
     switch (hd) {
         case 4: attn_fwd_kernel<4><<<grid, ATT_THREADS, 0, st>>>(qkv, cu_seqlens, keyvalid, out, lse, E, H, scale); break;
@@ -264,12 +273,15 @@ extern "C" int mvn_attention_fwd(const float* qkv, const int32_t* cu_seqlens, co
 extern "C" int mvn_attention_bwd(const float* qkv, const int32_t* cu_seqlens, const uint8_t* keyvalid, const float* out,
                                  const float* lse, const float* dout, float* dqkv, int B, int E, int H, float scale, int prec,
                                  void* stream) {
-    (void)prec;
     MVN_CHECK_ARG(qkv && cu_seqlens && out && lse && dout && dqkv && B > 0 && E > 0 && H > 0 && E % H == 0, "attention_bwd: bad arguments");
     MVN_CHECK_ARG(aligned16(qkv) && aligned16(dout) && aligned16(dqkv), "attention_bwd: buffers must be 16-byte aligned");
     const int hd = E / H;
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope prof(PROF_ATTN_BWD, st);
+    if (prec == 1 && keyvalid == nullptr) {
+        const int r = launch_attention_bwd_tc(qkv, cu_seqlens, out, lse, dout, dqkv, B, E, H, scale, st);
+        if (r != MVN_E_UNSUPPORTED) return r;
+    }
     const int grid = B * H;
     switch (hd) {
         case 4: attn_bwd_kernel<4><<<grid, ATT_THREADS, 0, st>>>(qkv, cu_seqlens, keyvalid, out, lse, dout, dqkv, E, H, scale); break;

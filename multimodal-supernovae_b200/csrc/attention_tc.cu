@@ -1,0 +1,339 @@
+// A3, tensor-core tier (prec==1): padding-masked self-attention over the packed token stream with the three
+// contractions (Q K^T, P V and their five backward counterparts) on warp-level tensor-core MMAs (m16n8k8, TF32
+// operands, fp32 accumulate) and the softmax in registers -- the T x T matrix lives only in accumulator fragments.
+//
+// Why warp-level mma and not tcgen05 here: the head dimension is 8 or 16, so one 16x8 score tile costs a single
+// MMA while its softmax costs ~6 instructions per score; the kernel is bound by the exp/scale pipeline, and a
+// TMEM round trip per score tile (tcgen05.ld / st) would add traffic without removing any of that work.
+//
+// One CTA per (sequence, head), 4 warps.  Forward: a warp owns 16 query rows, streams the keys in blocks of 64 with
+// an online softmax.  Backward: phase 1 (dQ, warp owns 16 queries, streams keys) and phase 2 (dK/dV, warp owns 16
+// keys, streams queries) recompute probabilities from the saved log-sum-exp; no atomics, deterministic.
+// The probability / dS accumulator fragments are fed back as the A operand of the next MMA without any shuffle by
+// relabelling the contraction index (k = t <-> column 2t, k = t+4 <-> column 2t+1) consistently on the B side.
+#include "common.cuh"
+
+namespace mvn {
+namespace {
+
+constexpr int ATC_THREADS = 128;
+constexpr int CH = 256;                       // keys (or queries) staged in shared memory at a time
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float tf32r(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+// D(16x8) += A(16x8, row) * B(8x8, col);  fragment layouts (g = lane/4, t = lane%4):
+//   a0:(g,t) a1:(g+8,t) a2:(g,t+4) a3:(g+8,t+4) ; b0:(k=t,n=g) b1:(k=t+4,n=g) ; c0:(g,2t) c1:(g,2t+1) c2:(g+8,2t) c3:(g+8,2t+1)
+__device__ __forceinline__ void mma_tf32(float* c, const float* a, float b0, float b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+                   "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+__device__ __forceinline__ float quad_max(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+// rows [row0, row0+cnt) of a column slice (HD floats at column `col`) of a row-major [*, ld] matrix -> smem
+// [cnt_pad8][HD+4] rounded to TF32 and multiplied by `mul`; rows up to the next multiple of 8 are zero-filled.
+template <int HD>
+__device__ __forceinline__ void load_slice(float* dst, const float* __restrict__ src, size_t ld, int col, int row0, int cnt, float mul) {
+    constexpr int LD = HD + 4;
+    const int pad = (cnt + 7) & ~7;
+    for (int idx = threadIdx.x; idx < pad * (HD / 4); idx += ATC_THREADS) {
+        const int j = idx / (HD / 4), d = (idx % (HD / 4)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < cnt) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)(row0 + j) * ld + col + d));
+        *reinterpret_cast<float4*>(dst + j * LD + d) = make_float4(tf32r(v.x * mul), tf32r(v.y * mul), tf32r(v.z * mul), tf32r(v.w * mul));
+    }
+}
+// A-operand fragments (16 rows starting at row0, HD columns) straight from global memory; rows >= limit read as 0.
+template <int HD>
+__device__ __forceinline__ void load_afrag(float (*a)[4], const float* __restrict__ src, size_t ld, int col, int row0, int limit, float mul, int g, int t) {
+#pragma unroll
+    for (int ks = 0; ks < HD / 8; ++ks) {
+        const int r_lo = row0 + g, r_hi = row0 + g + 8;
+        const float* p_lo = src + (size_t)r_lo * ld + col + ks * 8 + t;
+        const float* p_hi = src + (size_t)r_hi * ld + col + ks * 8 + t;
+        a[ks][0] = r_lo < limit ? tf32r(__ldg(p_lo) * mul) : 0.f;
+        a[ks][1] = r_hi < limit ? tf32r(__ldg(p_hi) * mul) : 0.f;
+        a[ks][2] = r_lo < limit ? tf32r(__ldg(p_lo + 4) * mul) : 0.f;
+        a[ks][3] = r_hi < limit ? tf32r(__ldg(p_hi + 4) * mul) : 0.f;
+    }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(ATC_THREADS) attn_fwd_mma_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ cu,
+                                                                   float* __restrict__ out, float* __restrict__ lse, int E, int H, float scale) {
+    constexpr int LD = HD + 4;
+    __shared__ __align__(16) float Ks[CH * LD];
+    __shared__ __align__(16) float Vs[CH * LD];
+    const int b = blockIdx.x / H, h = blockIdx.x % H;
+    const int r0 = cu[b], n = cu[b + 1] - r0;
+    if (n <= 0) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const size_t ld = 3 * (size_t)E;
+    const float* base = qkv + (size_t)r0 * ld;
+    const int nchunks = (n + CH - 1) / CH;
+    const int nrounds = (n + 63) / 64;
+
+    for (int rd = 0; rd < nrounds; ++rd) {
+        const int q0 = rd * 64 + warp * 16;
+        const bool active = q0 < n;
+        float qa[HD / 8][4];
+        load_afrag<HD>(qa, base, ld, h * HD, q0, n, scale * LOG2E, g, t);      // scores come out in log2 units
+        float o[HD / 8][4];
+#pragma unroll
+        for (int i = 0; i < HD / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+        float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+
+        for (int c = 0; c < nchunks; ++c) {
+            const int k0c = c * CH, kn = min(CH, n - k0c);
+            if (nchunks > 1 || rd == 0) {
+                __syncthreads();
+                load_slice<HD>(Ks, base, ld, E + h * HD, k0c, kn, 1.0f);
+                load_slice<HD>(Vs, base, ld, 2 * E + h * HD, k0c, kn, 1.0f);
+                __syncthreads();
+            }
+            if (!active) continue;
+            for (int kb = 0; kb < kn; kb += 64) {
+                float s[8][4];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int key0 = kb + j * 8;
+                    s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+                    if (key0 < kn) {
+#pragma unroll
+                        for (int ks = 0; ks < HD / 8; ++ks)
+                            mma_tf32(s[j], qa[ks], Ks[(key0 + g) * LD + ks * 8 + t], Ks[(key0 + g) * LD + ks * 8 + t + 4]);
+                    }
+                    const int kc = key0 + 2 * t;
+                    if (kc >= kn) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+                    if (kc + 1 >= kn) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+                }
+                float bm_lo = -INFINITY, bm_hi = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    bm_lo = fmaxf(bm_lo, fmaxf(s[j][0], s[j][1]));
+                    bm_hi = fmaxf(bm_hi, fmaxf(s[j][2], s[j][3]));
+                }
+                bm_lo = quad_max(bm_lo); bm_hi = quad_max(bm_hi);          // finite: key kb < kn is always live
+                const float mn_lo = fmaxf(m_lo, bm_lo), mn_hi = fmaxf(m_hi, bm_hi);
+                const float c_lo = exp2f(m_lo - mn_lo), c_hi = exp2f(m_hi - mn_hi);
+                m_lo = mn_lo; m_hi = mn_hi;
+                l_lo *= c_lo; l_hi *= c_hi;
+#pragma unroll
+                for (int i = 0; i < HD / 8; ++i) { o[i][0] *= c_lo; o[i][1] *= c_lo; o[i][2] *= c_hi; o[i][3] *= c_hi; }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int key0 = kb + j * 8;
+                    if (key0 >= kn) break;
+                    const float p0 = exp2f(s[j][0] - mn_lo), p1 = exp2f(s[j][1] - mn_lo);
+                    const float p2 = exp2f(s[j][2] - mn_hi), p3 = exp2f(s[j][3] - mn_hi);
+                    l_lo += p0 + p1; l_hi += p2 + p3;
+                    const float pa[4] = {tf32r(p0), tf32r(p2), tf32r(p1), tf32r(p3)};      // k=t <-> key 2t, k=t+4 <-> key 2t+1
+#pragma unroll
+                    for (int nt = 0; nt < HD / 8; ++nt)
+                        mma_tf32(o[nt], pa, Vs[(key0 + 2 * t) * LD + nt * 8 + g], Vs[(key0 + 2 * t + 1) * LD + nt * 8 + g]);
+                }
+            }
+        }
+        if (!active) continue;
+        l_lo = quad_sum(l_lo); l_hi = quad_sum(l_hi);
+        const float i_lo = 1.0f / l_lo, i_hi = 1.0f / l_hi;
+        const int q_lo = q0 + g, q_hi = q0 + g + 8;
+#pragma unroll
+        for (int nt = 0; nt < HD / 8; ++nt) {
+            if (q_lo < n) *reinterpret_cast<float2*>(out + (size_t)(r0 + q_lo) * E + h * HD + nt * 8 + 2 * t) = make_float2(o[nt][0] * i_lo, o[nt][1] * i_lo);
+            if (q_hi < n) *reinterpret_cast<float2*>(out + (size_t)(r0 + q_hi) * E + h * HD + nt * 8 + 2 * t) = make_float2(o[nt][2] * i_hi, o[nt][3] * i_hi);
+        }
+        if (t == 0) {
+            if (q_lo < n) lse[(size_t)(r0 + q_lo) * H + h] = (m_lo + log2f(l_lo)) * LN2;
+            if (q_hi < n) lse[(size_t)(r0 + q_hi) * H + h] = (m_hi + log2f(l_hi)) * LN2;
+        }
+    }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ cu,
+                                                                   const float* __restrict__ out, const float* __restrict__ lse,
+                                                                   const float* __restrict__ dout, float* __restrict__ dqkv,
+                                                                   int E, int H, float scale) {
+    constexpr int LD = HD + 4;
+    __shared__ __align__(16) float As[CH * LD];     // phase 1: K        phase 2: Q
+    __shared__ __align__(16) float Bs[CH * LD];     // phase 1: V        phase 2: dO
+    __shared__ float lse_s[CH];                     // phase 2: lse_i * log2e (+inf on padding rows)
+    __shared__ float D_s[CH];                       // phase 2: D_i = dO_i . O_i
+    const int b = blockIdx.x / H, h = blockIdx.x % H;
+    const int r0 = cu[b], n = cu[b + 1] - r0;
+    if (n <= 0) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const size_t ld = 3 * (size_t)E;
+    const float* base = qkv + (size_t)r0 * ld;
+    const float* obase = out + (size_t)r0 * E + h * HD;
+    const float* gbase = dout + (size_t)r0 * E + h * HD;
+    const int nchunks = (n + CH - 1) / CH;
+    const int nrounds = (n + 63) / 64;
+
+    // ---- phase 1: dQ_i = scale * sum_j P_ij (dO_i.V_j - D_i) K_j ; warp owns 16 queries -------------------------
+    for (int rd = 0; rd < nrounds; ++rd) {
+        const int q0 = rd * 64 + warp * 16;
+        const bool active = q0 < n;
+        const int q_lo = q0 + g, q_hi = q0 + g + 8;
+        float qa[HD / 8][4], ga[HD / 8][4];
+        load_afrag<HD>(qa, base, ld, h * HD, q0, n, scale * LOG2E, g, t);
+        load_afrag<HD>(ga, gbase, (size_t)E, 0, q0, n, 1.0f, g, t);
+        // D for rows g / g+8: each lane of the quad takes HD/4 of the dims
+        float D_lo = 0.f, D_hi = 0.f, L_lo = INFINITY, L_hi = INFINITY;
+#pragma unroll
+        for (int d = 0; d < HD / 4; ++d) {
+            const int dd = t * (HD / 4) + d;
+            if (q_lo < n) D_lo = fmaf(__ldg(gbase + (size_t)q_lo * E + dd), __ldg(obase + (size_t)q_lo * E + dd), D_lo);
+            if (q_hi < n) D_hi = fmaf(__ldg(gbase + (size_t)q_hi * E + dd), __ldg(obase + (size_t)q_hi * E + dd), D_hi);
+        }
+        D_lo = quad_sum(D_lo); D_hi = quad_sum(D_hi);
+        if (q_lo < n) L_lo = __ldg(lse + (size_t)(r0 + q_lo) * H + h) * LOG2E;
+        if (q_hi < n) L_hi = __ldg(lse + (size_t)(r0 + q_hi) * H + h) * LOG2E;
+        float dq[HD / 8][4];
+#pragma unroll
+        for (int i = 0; i < HD / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+
+        for (int c = 0; c < nchunks; ++c) {
+            const int k0c = c * CH, kn = min(CH, n - k0c);
+            if (nchunks > 1 || rd == 0) {
+                __syncthreads();
+                load_slice<HD>(As, base, ld, E + h * HD, k0c, kn, 1.0f);
+                load_slice<HD>(Bs, base, ld, 2 * E + h * HD, k0c, kn, 1.0f);
+                __syncthreads();
+            }
+            if (!active) continue;
+            const int ntile = (kn + 7) >> 3;
+            for (int j = 0; j < ntile; ++j) {
+                const int key0 = j * 8;
+                float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int ks = 0; ks < HD / 8; ++ks) {
+                    mma_tf32(s, qa[ks], As[(key0 + g) * LD + ks * 8 + t], As[(key0 + g) * LD + ks * 8 + t + 4]);
+                    mma_tf32(dp, ga[ks], Bs[(key0 + g) * LD + ks * 8 + t], Bs[(key0 + g) * LD + ks * 8 + t + 4]);
+                }
+                const int kc = key0 + 2 * t;
+                const bool v0 = kc < kn, v1 = kc + 1 < kn;
+                const float p0 = v0 ? exp2f(s[0] - L_lo) : 0.f, p1 = v1 ? exp2f(s[1] - L_lo) : 0.f;
+                const float p2 = v0 ? exp2f(s[2] - L_hi) : 0.f, p3 = v1 ? exp2f(s[3] - L_hi) : 0.f;
+                const float da[4] = {tf32r(p0 * (dp[0] - D_lo)), tf32r(p2 * (dp[2] - D_hi)), tf32r(p1 * (dp[1] - D_lo)), tf32r(p3 * (dp[3] - D_hi))};
+#pragma unroll
+                for (int nt = 0; nt < HD / 8; ++nt)
+                    mma_tf32(dq[nt], da, As[(key0 + 2 * t) * LD + nt * 8 + g], As[(key0 + 2 * t + 1) * LD + nt * 8 + g]);
+            }
+        }
+        if (!active) continue;
+#pragma unroll
+        for (int nt = 0; nt < HD / 8; ++nt) {
+            if (q_lo < n) *reinterpret_cast<float2*>(dqkv + (size_t)(r0 + q_lo) * ld + h * HD + nt * 8 + 2 * t) = make_float2(dq[nt][0] * scale, dq[nt][1] * scale);
+            if (q_hi < n) *reinterpret_cast<float2*>(dqkv + (size_t)(r0 + q_hi) * ld + h * HD + nt * 8 + 2 * t) = make_float2(dq[nt][2] * scale, dq[nt][3] * scale);
+        }
+    }
+
+    // ---- phase 2: dV_j = sum_i P_ij dO_i ; dK_j = scale * sum_i dS_ij Q_i ; warp owns 16 keys -----------------
+    for (int rd = 0; rd < nrounds; ++rd) {
+        const int k0 = rd * 64 + warp * 16;
+        const bool active = k0 < n;
+        float ka[HD / 8][4], va[HD / 8][4];
+        load_afrag<HD>(ka, base, ld, E + h * HD, k0, n, scale * LOG2E, g, t);
+        load_afrag<HD>(va, base, ld, 2 * E + h * HD, k0, n, 1.0f, g, t);
+        float dk[HD / 8][4], dv[HD / 8][4];
+#pragma unroll
+        for (int i = 0; i < HD / 8; ++i) { dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; }
+
+        for (int c = 0; c < nchunks; ++c) {
+            const int q0c = c * CH, qn = min(CH, n - q0c);
+            if (nchunks > 1 || rd == 0) {
+                __syncthreads();                    // also orders phase-1 readers of As/Bs before the overwrite
+                load_slice<HD>(As, base, ld, h * HD, q0c, qn, 1.0f);
+                load_slice<HD>(Bs, gbase, (size_t)E, 0, q0c, qn, 1.0f);
+                const int pad = (qn + 7) & ~7;
+                for (int i = threadIdx.x; i < pad; i += ATC_THREADS) {
+                    float Di = 0.f, Li = INFINITY;
+                    if (i < qn) {
+#pragma unroll
+                        for (int d = 0; d < HD; d += 4) {
+                            const float4 gv = __ldg(reinterpret_cast<const float4*>(gbase + (size_t)(q0c + i) * E + d));
+                            const float4 ov = __ldg(reinterpret_cast<const float4*>(obase + (size_t)(q0c + i) * E + d));
+                            Di = fmaf(gv.x, ov.x, fmaf(gv.y, ov.y, fmaf(gv.z, ov.z, fmaf(gv.w, ov.w, Di))));
+                        }
+                        Li = __ldg(lse + (size_t)(r0 + q0c + i) * H + h) * LOG2E;
+                    }
+                    D_s[i] = Di; lse_s[i] = Li;
+                }
+                __syncthreads();
+            }
+            if (!active) continue;
+            const int ntile = (qn + 7) >> 3;
+            for (int j = 0; j < ntile; ++j) {
+                const int qq = j * 8;
+                float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};      // transposed tiles: rows = keys, cols = queries
+#pragma unroll
+                for (int ks = 0; ks < HD / 8; ++ks) {
+                    mma_tf32(s, ka[ks], As[(qq + g) * LD + ks * 8 + t], As[(qq + g) * LD + ks * 8 + t + 4]);
+                    mma_tf32(dp, va[ks], Bs[(qq + g) * LD + ks * 8 + t], Bs[(qq + g) * LD + ks * 8 + t + 4]);
+                }
+                const int qc = qq + 2 * t;
+                const float L0 = lse_s[qc], L1 = lse_s[qc + 1], D0 = D_s[qc], D1 = D_s[qc + 1];
+                const float p0 = exp2f(s[0] - L0), p1 = exp2f(s[1] - L1), p2 = exp2f(s[2] - L0), p3 = exp2f(s[3] - L1);   // 0 on padding (L=+inf)
+                const float pa[4] = {tf32r(p0), tf32r(p2), tf32r(p1), tf32r(p3)};
+                const float da[4] = {tf32r(p0 * (dp[0] - D0)), tf32r(p2 * (dp[2] - D0)), tf32r(p1 * (dp[1] - D1)), tf32r(p3 * (dp[3] - D1))};
+#pragma unroll
+                for (int nt = 0; nt < HD / 8; ++nt) {
+                    mma_tf32(dv[nt], pa, Bs[(qq + 2 * t) * LD + nt * 8 + g], Bs[(qq + 2 * t + 1) * LD + nt * 8 + g]);
+                    mma_tf32(dk[nt], da, As[(qq + 2 * t) * LD + nt * 8 + g], As[(qq + 2 * t + 1) * LD + nt * 8 + g]);
+                }
+            }
+        }
+        if (!active) continue;
+        const int k_lo = k0 + g, k_hi = k0 + g + 8;
+#pragma unroll
+        for (int nt = 0; nt < HD / 8; ++nt) {
+            const int col = h * HD + nt * 8 + 2 * t;
+            if (k_lo < n) {
+                *reinterpret_cast<float2*>(dqkv + (size_t)(r0 + k_lo) * ld + E + col) = make_float2(dk[nt][0] * scale, dk[nt][1] * scale);
+                *reinterpret_cast<float2*>(dqkv + (size_t)(r0 + k_lo) * ld + 2 * E + col) = make_float2(dv[nt][0], dv[nt][1]);
+            }
+            if (k_hi < n) {
+                *reinterpret_cast<float2*>(dqkv + (size_t)(r0 + k_hi) * ld + E + col) = make_float2(dk[nt][2] * scale, dk[nt][3] * scale);
+                *reinterpret_cast<float2*>(dqkv + (size_t)(r0 + k_hi) * ld + 2 * E + col) = make_float2(dv[nt][2], dv[nt][3]);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// Returns MVN_E_UNSUPPORTED for head dims the MMA kernels are not built for (caller falls back to the fp32 kernel).
+int launch_attention_fwd_tc(const float* qkv, const int32_t* cu, float* out, float* lse, int B, int E, int H, float scale, cudaStream_t st) {
+    const int hd = E / H;
+    if (hd == 8) attn_fwd_mma_kernel<8><<<B * H, ATC_THREADS, 0, st>>>(qkv, cu, out, lse, E, H, scale);
+    else if (hd == 16) attn_fwd_mma_kernel<16><<<B * H, ATC_THREADS, 0, st>>>(qkv, cu, out, lse, E, H, scale);
+    else return MVN_E_UNSUPPORTED;
+    MVN_LAUNCH_CHECK();
+    return 0;
+}
+int launch_attention_bwd_tc(const float* qkv, const int32_t* cu, const float* out, const float* lse, const float* dout, float* dqkv,
+                            int B, int E, int H, float scale, cudaStream_t st) {
+    const int hd = E / H;
+    if (hd == 8) attn_bwd_mma_kernel<8><<<B * H, ATC_THREADS, 0, st>>>(qkv, cu, out, lse, dout, dqkv, E, H, scale);
+    else if (hd == 16) attn_bwd_mma_kernel<16><<<B * H, ATC_THREADS, 0, st>>>(qkv, cu, out, lse, dout, dqkv, E, H, scale);
+    else return MVN_E_UNSUPPORTED;
+    MVN_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace mvn

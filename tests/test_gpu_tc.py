@@ -145,3 +145,31 @@ def test_tc_seq_encoder_vs_oracle(case):
     print(f"tf32 tier {case}: fwd relerr {e_fwd:.3e}, worst grad relerr {worst[0]:.3e} ({worst[1]})")
     assert e_fwd < TOL_TC
     assert worst[0] < 1e-2, worst
+
+
+@pytest.mark.parametrize("E,H,lens", [(64, 8, [120, 1, 37, 200, 64, 8, 129]), (32, 2, [220, 165, 16, 7, 255, 256]), (32, 2, [300, 1024, 513, 9])])
+def test_tc_attention_fwd_bwd(L, E, H, lens):
+    """packed-stream attention on tensor cores vs torch fp64 per sequence (softmax(QK^T/sqrt(E)) V and its gradients)."""
+    torch.manual_seed(len(lens) * E)
+    hd = E // H
+    B, M = len(lens), sum(lens)
+    qkv = torch.randn(M, 3 * E); dout = torch.randn(M, E)
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32)
+    ref = qkv.double().requires_grad_()
+    outs = []
+    for b in range(B):
+        r = ref[cu[b]:cu[b + 1]]
+        q, k, v = (r[:, i * E:(i + 1) * E].reshape(-1, H, hd).transpose(0, 1) for i in range(3))
+        p = torch.softmax(q @ k.transpose(1, 2) / math.sqrt(E), dim=-1)
+        outs.append((p @ v).transpose(0, 1).reshape(-1, E))
+    oref = torch.cat(outs)
+    oref.backward(dout.double())
+    qg, cug, dg = qkv.to(dev()), cu.to(dev()), dout.to(dev())
+    out = torch.empty(M, E, device=dev()); lse = torch.empty(M, H, device=dev()); dqkv = torch.full((M, 3 * E), float("nan"), device=dev())
+    sc = 1 / math.sqrt(E)
+    assert L.mvn_attention_fwd(P(qg), P(cug), None, P(out), P(lse), B, E, H, sc, 1, S()) == 0, L.mvn_last_error()
+    assert L.mvn_attention_bwd(P(qg), P(cug), None, P(out), P(lse), P(dg), P(dqkv), B, E, H, sc, 1, S()) == 0, L.mvn_last_error()
+    torch.cuda.synchronize()
+    assert relerr(out, oref) < TOL_TC
+    assert torch.isfinite(dqkv).all()
+    assert relerr(dqkv, ref.grad) < 2e-3
