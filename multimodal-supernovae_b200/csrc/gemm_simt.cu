@@ -8,6 +8,9 @@ namespace mvn {
 int launch_gemm_tc(const float* A, const float* Bm, float* C, const int32_t* n_rows_dev, int M_cap, int N, int K,
                    bool b_is_nk, const GemmEpilogue& ep, cudaStream_t st);   // gemm_tc.cu; returns MVN_E_UNSUPPORTED if shape not covered
 
+int launch_wgrad_tc(const float* dY, const float* X, const int32_t* n_rows_dev, int M_cap, int N, int K, float* partial, size_t pstride,
+                    size_t woff, long long boff, cudaStream_t st);             // gemm_tc.cu
+
 namespace {
 
 constexpr int BK = 16;
@@ -223,18 +226,33 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ dY
     if (do_bias && tid < 64 && n0 + tid < N) p[boff + n0 + tid] = bsum;
 }
 
+// out[i] = sum over slabs of partial[s][i]: a block owns 32 consecutive columns, its 8 warps split the slabs (16 independent
+// loads in flight per thread), fixed summation order -> deterministic.
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, size_t pstride, size_t n,
                                                               int nslabs, float* __restrict__ out, int accumulate) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    __shared__ float red[8][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t i = (size_t)blockIdx.x * 32 + lane;
+    float acc = 0.f;
+    if (i < n) {
+        const int per = (nslabs + 7) / 8;
+        const int s0 = warp * per, s1 = min(nslabs, s0 + per);
         const float* p = partial + i;
-        int s = 0;
-        for (; s + 3 < nslabs; s += 4) {
-            s0 += p[(size_t)(s + 0) * pstride]; s1 += p[(size_t)(s + 1) * pstride];
-            s2 += p[(size_t)(s + 2) * pstride]; s3 += p[(size_t)(s + 3) * pstride];
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int s = s0;
+        for (; s + 3 < s1; s += 4) {
+            a0 += p[(size_t)(s + 0) * pstride]; a1 += p[(size_t)(s + 1) * pstride];
+            a2 += p[(size_t)(s + 2) * pstride]; a3 += p[(size_t)(s + 3) * pstride];
         }
-        for (; s < nslabs; ++s) s0 += p[(size_t)s * pstride];
-        const float v = (s0 + s1) + (s2 + s3);
+        for (; s < s1; ++s) a0 += p[(size_t)s * pstride];
+        acc = (a0 + a1) + (a2 + a3);
+    }
+    red[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && i < n) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[w][lane];
         out[i] = accumulate ? out[i] + v : v;
     }
 }
@@ -274,9 +292,12 @@ int launch_gemm(const float* A, const float* Bm, float* C, const int32_t* n_rows
 
 int launch_wgrad_partials(const float* dY, const float* X, const int32_t* n_rows_dev, int M_cap, int N, int K,
                           float* partial, size_t pstride, size_t woff, long long boff, int prec, cudaStream_t st) {
-    (void)prec;
     MVN_CHECK_ARG(dY && X && partial && M_cap > 0 && N > 0 && K > 0, "wgrad: null pointer or non-positive size");
     ProfScope prof(PROF_WGRAD, st);
+    if (prec == 1) {
+        const int r = launch_wgrad_tc(dY, X, n_rows_dev, M_cap, N, K, partial, pstride, woff, boff, st);
+        if (r != MVN_E_UNSUPPORTED) return r;
+    }
     dim3 grid(kSlabs, cdiv(N, 64), cdiv(K, 64));
     wgrad_kernel<<<grid, 256, 0, st>>>(dY, X, n_rows_dev, M_cap, N, K, partial, pstride, woff, boff,
                                        (N % 4 == 0) && aligned16(dY), (K % 4 == 0) && aligned16(X));
@@ -287,7 +308,7 @@ int launch_wgrad_partials(const float* dY, const float* X, const int32_t* n_rows
 int launch_reduce_partials(const float* partial, size_t pstride, size_t n, float* out, int accumulate, cudaStream_t st) {
     if (n == 0) return 0;
     ProfScope prof(PROF_ROW, st);
-    const int blocks = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+    const int blocks = (int)((n + 31) / 32);
     reduce_partials_kernel<<<blocks, 256, 0, st>>>(partial, pstride, n, kSlabs, out, accumulate);
     MVN_LAUNCH_CHECK();
     return 0;

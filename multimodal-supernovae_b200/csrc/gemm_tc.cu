@@ -40,7 +40,7 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 struct Key {
-    const void* p; int rows, cols, box;
+    const void* p; int rows, cols, box;      // box < 0 encodes the 32-byte-atom swizzle
     bool operator==(const Key& o) const { return p == o.p && rows == o.rows && cols == o.cols && box == o.box; }
 };
 struct KeyHash {
@@ -52,9 +52,9 @@ std::mutex g_mu;
 std::unordered_map<Key, CUtensorMap*, KeyHash> g_maps;
 }  // namespace
 
-const CUtensorMap* get_tmap_2d(const float* base, int rows, int cols, int box_rows) {
+const CUtensorMap* get_tmap_2d(const float* base, int rows, int cols, int box_rows, bool atom32) {
     std::lock_guard<std::mutex> lk(g_mu);
-    Key k{base, rows, cols, box_rows};
+    Key k{base, rows, cols, atom32 ? -box_rows : box_rows};
     auto it = g_maps.find(k);
     if (it != g_maps.end()) return it->second;
     EncodeTiledFn fn = encode_fn();
@@ -69,7 +69,7 @@ const CUtensorMap* get_tmap_2d(const float* base, int rows, int cols, int box_ro
     cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1u, 1u};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d) for [%d x %d] box %d", (int)r, rows, cols, box_rows);
         delete m;
@@ -374,6 +374,160 @@ int launch_tc(const CUtensorMap& tm, const TcArgs& a, cudaStream_t st) {
     return 0;
 }
 
+
+// ==========================================================================================================
+// Weight-gradient GEMM on tcgen05:  dW[N,K] = dY^T X,  db[N] = colsum(dY)   (contraction over the token stream).
+// Both operands are "MN-major" for the MMA (the contraction index -- the token -- is the slow dimension of the
+// row-major activations).  For 32-bit MN-major operands the tensor core accepts exactly one shared-memory layout,
+// the 128-byte swizzle with 32-byte atoms (descriptor layout type 1; 32-B chunk index XOR (row & 3), 4-row atoms),
+// which is what a TMA box of [32 tokens x 32 floats] with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B writes -- so the
+// activations go HBM -> TMA -> smem -> tensor core with no transpose anywhere.
+//   D[n, k] (TMEM, lanes = n in blocks of 128, columns = k)  +=  A[n, tok] * B[tok, k]     8 tokens per MMA
+//   db rides along as a second tiny MMA against a constant block of ones (N=16 columns, column 0 is read back).
+// The accumulators stay in TMEM for the CTA's whole token range; each CTA writes one slab of partials
+// (deterministic: launch_reduce_partials sums the kSlabs slabs in a fixed order).
+constexpr int WG_TOK = 32;                         // tokens per pipeline stage
+constexpr int WG_BOX = WG_TOK * 128;               // bytes of one [32 tok x 32 float] box
+constexpr int WG_RING = 200 * 1024;
+constexpr int WG_OFF_ONES = WG_RING + 16 * 1024;   // slack: an M=128 A operand may over-read up to 16 KB of don't-care rows
+constexpr int WG_OFF_BAR = WG_OFF_ONES + 1024;
+constexpr int WG_MAXSTAGE = 8;
+constexpr int WG_OFF_TMEMPTR = WG_OFF_BAR + (2 * WG_MAXSTAGE + 1) * 8;
+constexpr int WG_SMEM = WG_OFF_TMEMPTR + 16 + 1024;
+constexpr int WG_THREADS = 192;
+
+struct WgArgs {
+    const int32_t* n_rows_dev;
+    int M_cap, N, K;
+    float* partial; size_t pstride, woff; long long boff;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapY, const __grid_constant__ CUtensorMap tmapX,
+                                                                 const WgArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int N = a.N, K = a.K;
+    const int NB = N >> 5, KB = K >> 5;                       // 32-wide boxes of dY and X per stage
+    const int MB = (N + 127) >> 7;                            // 128-row accumulator blocks
+    const int stage_bytes = (NB + KB) * WG_BOX;
+    const int nstage = min(WG_MAXSTAGE, WG_RING / stage_bytes);
+    const int rows = a.n_rows_dev ? min(*a.n_rows_dev, a.M_cap) : a.M_cap;
+    const int ntiles = (rows + WG_TOK - 1) / WG_TOK;
+    const int bias_col = MB * K;
+
+    const uint32_t bar0 = sbase + WG_OFF_BAR;
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (WG_MAXSTAGE + s); };
+    const uint32_t done_bar = bar0 + 8u * (2 * WG_MAXSTAGE);
+    volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + WG_OFF_TMEMPTR);
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmapY);
+        tma_prefetch_desc(&tmapX);
+        for (int s = 0; s < WG_MAXSTAGE; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(done_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(sbase + WG_OFF_TMEMPTR, TMEM_COLS);
+    for (int i = threadIdx.x; i < 256; i += WG_THREADS) reinterpret_cast<float*>(smem + WG_OFF_ONES)[i] = 1.0f;
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const bool have_work = (int)blockIdx.x < ntiles;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int s = it % nstage;
+                mbar_wait(empty_bar(s), ((it / nstage) & 1) ^ 1);
+                mbar_expect_tx(full_bar(s), stage_bytes);
+                const uint32_t dst = sbase + s * stage_bytes;
+                for (int nb = 0; nb < NB; ++nb) tma_load_2d(dst + nb * WG_BOX, &tmapY, full_bar(s), nb * 32, tile * WG_TOK);
+                for (int kb = 0; kb < KB; ++kb) tma_load_2d(dst + (NB + kb) * WG_BOX, &tmapX, full_bar(s), kb * 32, tile * WG_TOK);
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = idesc_tf32(128, K, 1, 1);
+        const uint32_t idesc_b = idesc_tf32(128, 16, 1, 1);
+        const uint64_t ones_desc = smem_desc_sw128_mn32(sbase + WG_OFF_ONES, WG_BOX, 512);
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int s = it % nstage;
+            mbar_wait(full_bar(s), (it / nstage) & 1);
+            const uint32_t st_addr = sbase + s * stage_bytes;
+            const int live = rows - tile * WG_TOK;                   // tokens of this tile below the device-side row count
+            if (live < WG_TOK) {
+                // boundary tile: rows past the live count hold stale workspace data -> zero them (every box, whole 128-B rows)
+                float4* st = reinterpret_cast<float4*>(smem + s * stage_bytes);
+                for (int bx = 0; bx < NB + KB; ++bx)
+                    for (int i = live * 8 + lane; i < WG_TOK * 8; i += 32) st[bx * (WG_BOX / 16) + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                fence_proxy_async();
+                __syncwarp();
+            }
+            tc_fence_after();
+            if (lane == 0) {
+#pragma unroll
+                for (int ks = 0; ks < WG_TOK / 8; ++ks) {
+                    const uint64_t bdesc = smem_desc_sw128_mn32(st_addr + NB * WG_BOX + ks * 1024, WG_BOX, 512);
+                    for (int mb = 0; mb < MB; ++mb) {
+                        const uint64_t adesc = smem_desc_sw128_mn32(st_addr + mb * 4 * WG_BOX + ks * 1024, WG_BOX, 512);
+                        umma_tf32(tmem_base + mb * K, adesc, bdesc, idesc, (it | ks) != 0);
+                        if (a.boff >= 0) umma_tf32(tmem_base + bias_col + mb * 16, adesc, ones_desc, idesc_b, (it | ks) != 0);
+                    }
+                }
+                umma_commit(empty_bar(s));
+            }
+            __syncwarp();
+        }
+        if (lane == 0) umma_commit(done_bar);
+        __syncwarp();
+    } else {
+        // ===== final epilogue: TMEM accumulators -> this CTA's slab of partials =====
+        const int quad = warp & 3;
+        float* p = a.partial + (size_t)blockIdx.x * a.pstride;
+        if (have_work) {
+            mbar_wait(done_bar, 0);
+            tc_fence_after();
+        }
+        for (int mb = 0; mb < MB; ++mb) {
+            const int n = mb * 128 + quad * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+            for (int c0 = 0; c0 < K; c0 += 32) {
+                float v[32];
+                if (have_work) {
+                    tmem_ld32(taddr + mb * K + c0, v);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                }
+                if (n < N) {
+                    float4* dst = reinterpret_cast<float4*>(p + a.woff + (size_t)n * K + c0);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) dst[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+            }
+            if (a.boff >= 0) {
+                float v[16];
+                if (have_work) {
+                    tmem_ld16(taddr + bias_col + mb * 16, v);
+                } else {
+                    v[0] = 0.f;
+                }
+                if (n < N) p[a.boff + n] = v[0];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
 }  // namespace
 
 int launch_gemm_tc(const float* A, const float* Bm, float* C, const int32_t* n_rows_dev, int M_cap, int N, int K, bool b_is_nk,
@@ -387,7 +541,7 @@ int launch_gemm_tc(const float* A, const float* Bm, float* C, const int32_t* n_r
         (ep.xhat && !aligned16(ep.xhat)))
         return MVN_E_UNSUPPORTED;
     if (ln) MVN_CHECK_ARG(ep.beta != nullptr, "gemm+LN: beta missing");
-    const CUtensorMap* tm = get_tmap_2d(A, M_cap, K, TILE_M);
+    const CUtensorMap* tm = get_tmap_2d(A, M_cap, K, TILE_M, false);
     if (!tm) return MVN_E_BADARG;
     TcArgs a;
     a.B = Bm; a.C = C; a.n_rows_dev = n_rows_dev; a.M_cap = M_cap; a.N = N; a.K = K; a.b_is_nk = b_is_nk ? 1 : 0; a.ep = ep;
@@ -395,4 +549,26 @@ int launch_gemm_tc(const float* A, const float* Bm, float* C, const int32_t* n_r
     return N == 32 ? launch_tc<1>(*tm, a, st) : launch_tc<2>(*tm, a, st);
 }
 
+}  // namespace mvn
+
+namespace mvn {
+// returns MVN_E_UNSUPPORTED when the shape is outside what tc_wgrad_kernel covers (caller uses the FFMA kernel)
+int launch_wgrad_tc(const float* dY, const float* X, const int32_t* n_rows_dev, int M_cap, int N, int K, float* partial, size_t pstride,
+                    size_t woff, long long boff, cudaStream_t st) {
+    if (N % 32 != 0 || K % 32 != 0 || N > 256 || K > 256 || N + K > 320 || M_cap < 128) return MVN_E_UNSUPPORTED;
+    if (!aligned16(dY) || !aligned16(X) || !aligned16(partial) || (pstride % 4) != 0 || (woff % 4) != 0) return MVN_E_UNSUPPORTED;
+    const CUtensorMap* ty = tc::get_tmap_2d(dY, M_cap, N, WG_TOK, true);
+    const CUtensorMap* tx = tc::get_tmap_2d(X, M_cap, K, WG_TOK, true);
+    if (!ty || !tx) return MVN_E_BADARG;
+    static bool configured = false;
+    if (!configured) {
+        MVN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
+        configured = true;
+    }
+    WgArgs a;
+    a.n_rows_dev = n_rows_dev; a.M_cap = M_cap; a.N = N; a.K = K; a.partial = partial; a.pstride = pstride; a.woff = woff; a.boff = boff;
+    tc_wgrad_kernel<<<kSlabs, WG_THREADS, WG_SMEM, st>>>(*ty, *tx, a);
+    MVN_LAUNCH_CHECK();
+    return 0;
+}
 }  // namespace mvn

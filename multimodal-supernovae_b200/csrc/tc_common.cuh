@@ -115,8 +115,7 @@ __device__ __forceinline__ float to_tf32(float x) {
 // swizzle atom, chunk (16 B) index XORed with (row & 7) -- exactly what a TMA box with a 128-byte inner extent and
 // CU_TENSOR_MAP_SWIZZLE_128B writes.
 //   K-major operand  (row = M/N index, 128 B = 32 fp32 along K): SBO = 1024 (next 8 rows), LBO unused.
-//   MN-major operand (row = K index, 128 B = 32 fp32 along M/N): SBO = 1024 (next 8 k), LBO = bytes between
-//   successive 32-wide M/N blocks.
+// (MN-major 32-bit operands cannot use this layout: see smem_desc_sw128_mn32.)
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
@@ -124,6 +123,19 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
     d |= (uint64_t)1 << 46;          // descriptor version (sm_100)
     d |= (uint64_t)2 << 61;          // SWIZZLE_128B
+    return d;
+}
+// MN-major operand of 32-bit elements (row = K index, 128 B = 32 fp32 along M/N): the only accepted layout is the
+// 128-byte swizzle with 32-byte atoms -- 32-B chunk index XOR (row & 3), atoms of 4 rows -- written by TMA with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  SBO = bytes between successive 4-row groups (512 for dense 128-B rows),
+// LBO = bytes between successive 32-wide M/N blocks.
+__device__ __forceinline__ uint64_t smem_desc_sw128_mn32(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;          // SWIZZLE_128B_BASE32B
     return d;
 }
 // Instruction descriptor for kind::tf32, fp32 accumulate.  a_mn / b_mn: 1 = operand is MN-major ("transposed").
@@ -138,9 +150,10 @@ __device__ __forceinline__ uint32_t sw128_off(uint32_t row, uint32_t col) {
 }
 
 // ---- host: tensor maps ---------------------------------------------------------------------------------
-// Row-major fp32 matrix [rows, cols] (cols contiguous); box = 32 columns (128 B) x box_rows rows; 128B swizzle.
+// Row-major fp32 matrix [rows, cols] (cols contiguous); box = 32 columns (128 B) x box_rows rows; 128B swizzle
+// (16-byte atoms, or 32-byte atoms when atom32 -- the layout MN-major tf32 operands need).
 // Returns a pointer to a cached map (valid for the life of the process) or nullptr with the error text set.
-const CUtensorMap* get_tmap_2d(const float* base, int rows, int cols, int box_rows);
+const CUtensorMap* get_tmap_2d(const float* base, int rows, int cols, int box_rows, bool atom32);
 
 }  // namespace tc
 }  // namespace mvn

@@ -114,7 +114,7 @@ def test_tc_linear_bwd_weight(L, M, N, K):
     assert L.mvn_linear_bwd_weight(P(dyg), P(xg), P(dw), P(db), None, M, N, K, 0, P(ws), wsb, 1, S()) == 0, L.mvn_last_error()
     torch.cuda.synchronize()
     assert relerr(dw, ref_w) < TOL_TC
-    assert relerr(db, ref_b) < 1e-5
+    assert relerr(db, ref_b) < 2e-3          # colsum rides on the same TF32 MMA (against a block of ones)
 
 
 @pytest.mark.parametrize("case", ["lc", "sp"])
