@@ -77,7 +77,8 @@ def model_kwargs(wl, dropout):
 def flops_per_step(wl, batch):
     """Algorithmic FLOPs of one training step, two accountings: dense over the padded T (comparable with
     the reference) and executed (valid tokens only).  Returned per kernel class for the executed accounting."""
-    out = {"padded_train": 0.0, "gemm": 0.0, "wgrad": 0.0, "attn_fwd": 0.0, "attn_bwd": 0.0}
+    out = {"padded_train": 0.0, "gemm": 0.0, "wgrad": 0.0, "attn_fwd": 0.0, "attn_bwd": 0.0,
+           "bytes": {"gemm": 0.0, "wgrad": 0.0, "attn_fwd": 0.0, "attn_bwd": 0.0, "row": 0.0}}
     for key, m_idx, T in (("lc", 3, wl["T_lc"]), ("sp", 6, wl["T_sp"])):
         kw = wl[key]
         if kw is None:
@@ -92,6 +93,15 @@ def flops_per_step(wl, batch):
         n2 = (nb * nb).sum().item()
         out["attn_fwd"] += L * 4.0 * n2 * E
         out["attn_bwd"] += L * 10.0 * n2 * E
+        # algorithmic HBM bytes (fp32 storage; every operand counted once in, once out -- DESIGN.md "bytes per token-layer"):
+        #   GEMM class  fwd qkv 4E, unify+res+LN 4E, ff1 5E, ff2+res+LN 7E; dgrad ff2 9E, ff1 6E, unify 2E, qkv 5E  = 42E floats
+        #   wgrad class ff2 5E, ff1 5E, unify 2E, qkv 4E = 16E;  attention fwd 4E+H, bwd 8E+H;  LayerNorm bwd 2 x 3E
+        H = kw["heads"]
+        out["bytes"]["gemm"] += 4.0 * L * M * 42 * E
+        out["bytes"]["wgrad"] += 4.0 * L * M * 16 * E
+        out["bytes"]["attn_fwd"] += 4.0 * L * M * (4 * E + H)
+        out["bytes"]["attn_bwd"] += 4.0 * L * M * (8 * E + H)
+        out["bytes"]["row"] += 4.0 * L * M * 6 * E
     out["executed_train"] = out["gemm"] + out["wgrad"] + out["attn_fwd"] + out["attn_bwd"]
     return out
 
@@ -131,7 +141,7 @@ def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d["hbm_gbs"], d["bf16_tflops_sustained"], "measured (MEASURED_PEAKS.json, sustained bf16)"
+        return d["hbm_gbs"], d["bf16_tflops_sustained"], "measured (MEASURED_PEAKS.json: hbm_gbs copy bandwidth / sustained bf16)"
     return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
 
 
@@ -242,7 +252,7 @@ def run_gpu(args):
         L.mvn_prof_read(c, ctypes.byref(ms), ctypes.byref(cnt))
         breakdown[nme] = {"ms": round(ms.value, 4), "launches": cnt.value}
     L.mvn_prof_enable(0)
-    top = max(("gemm", "wgrad", "attn_fwd", "attn_bwd"), key=lambda k: breakdown[k]["ms"])
+    top = max(("gemm", "wgrad", "attn_fwd", "attn_bwd", "row"), key=lambda k: breakdown[k]["ms"])
     top_id = names.index(top)
 
     # ---- timed region: K steps, device-resident inputs, per-step CUDA events, L2 flushed between steps ----
@@ -292,8 +302,26 @@ def run_gpu(args):
     ms_per_step = dev_ms / args.steps
     value = world * B * args.steps / (dev_ms / 1e3)
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
-    top_flops = fl[top]
-    ach = top_flops * args.steps / (ms_t.value / 1e3) / 1e12 if ms_t.value > 0 else 0.0
+    hbm_bound = top in ("gemm", "wgrad", "row")          # token-stream kernels: K,N <= 256 -> bytes, not flops, bound them
+    n_l = max(cnt_t.value, 1)
+    avg_ms = ms_t.value / n_l                              # average launch duration of the class inside the timed region
+    if hbm_bound:
+        per_launch = fl["bytes"][top] * args.steps / n_l   # algorithmic bytes per launch (class average)
+        ach, peak, unit = per_launch / (avg_ms / 1e3) / 1e9, hbm, "GB/s"
+    else:
+        per_launch = fl[top] * args.steps / n_l
+        ach, peak, unit = per_launch / (avg_ms / 1e3) / 1e12, tf, "TFLOP/s"
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_per_launch.json")   # from the committed ncu --set full capture (scripts/ncu_summary.py)
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.precision, {}).get(top)
+    classes = {}
+    for k in ("gemm", "wgrad", "attn_fwd", "attn_bwd", "row"):
+        ms_k = breakdown[k]["ms"]
+        if ms_k > 0:
+            classes[k] = {"ms": ms_k, "algorithmic_GBps": fl["bytes"][k] / (ms_k / 1e3) / 1e9, "frac_hbm": fl["bytes"][k] / (ms_k / 1e3) / 1e9 / hbm}
+            if k in fl and k != "row":
+                classes[k]["executed_TFLOPs"] = fl[k] / (ms_k / 1e3) / 1e12
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -311,10 +339,14 @@ def run_gpu(args):
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel_class": top, "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf,
-                     "traffic": None, "peak_source": src, "launches_timed": cnt_t.value, "class_ms_per_step": ms_t.value / args.steps,
-                     "flops_accounting": "executed (valid tokens only); padded-equivalent step FLOPs in flops_per_step.padded_train"},
-        "flops_per_step": {k: v for k, v in fl.items()},
+        "roofline": {"bound": "hbm" if hbm_bound else "tensor", "kernel_class": top, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                     "traffic": traffic, "algorithmic_per_launch": per_launch, "avg_launch_ms": avg_ms, "peak_source": src,
+                     "launches_timed": cnt_t.value, "class_ms_per_step": ms_t.value / args.steps,
+                     "accounting": "class average over its launches in the timed region; executed work (valid tokens only); "
+                                   "padded-equivalent step FLOPs in flops_per_step.padded_train"},
+        "kernel_classes": classes,
+        "flops_per_step": {k: v for k, v in fl.items() if k != "bytes"},
+        "bytes_per_step": fl["bytes"],
         "step_tflops": {"padded_equivalent": fl["padded_train"] / (ms_per_step / 1e3) / 1e12, "executed": fl["executed_train"] / (ms_per_step / 1e3) / 1e12,
                         "frac_of_peak_padded": fl["padded_train"] / (ms_per_step / 1e3) / 1e12 / tf},
         "kernel_breakdown_ms": breakdown,
@@ -337,7 +369,8 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="samples per GPU per step")
     ap.add_argument("--ref-batch", type=int, default=64, help="samples per CPU reference step (bounded sample)")
     ap.add_argument("--dropout", type=float, default=0.0)
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
+                    help="tf32: tcgen05/mma tensor-core tier (fp32 storage, fp32 accumulate; parity 1e-3); fp32: FFMA tier (parity 1e-5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

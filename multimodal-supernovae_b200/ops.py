@@ -537,14 +537,45 @@ def _all_gather_rows(t: torch.Tensor, group) -> torch.Tensor:
     return out
 
 
+def _clip_fwd_local(e1, e2, e1_all, e2_all, n, N, D, off, ls, lb, prec):
+    """This rank's rows/columns of the streamed loss: (loss share [1], lse [2, n]) -- mvn_clip_loss_fwd."""
+    L = lib()
+    e1 = _req(e1, "embs1"); e2 = _req(e2, "embs2"); ls = _req(ls, "logit_scale"); lb = _req(lb, "logit_bias")
+    wsb = L.mvn_clip_loss_workspace_bytes(n, N, D)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=e1.device)
+    loss = torch.empty(1, dtype=torch.float32, device=e1.device)
+    lse = torch.empty(2, n, dtype=torch.float32, device=e1.device)
+    check(L.mvn_clip_loss_fwd(_p(e1), _p(e2), _p(e1_all), _p(e2_all), n, N, D, off, _p(ls), _p(lb), _p(loss), _p(lse[0]), _p(lse[1]),
+                              _p(ws), wsb, prec, _stream()), "clip_loss_fwd")
+    _count(4)
+    return loss, lse
+
+
+def _clip_bwd_local(e1, e2, e1_all, e2_all, n, N, D, off, ls, lb, lse_all, g, prec):
+    """(d_e1_local, d_e2_local, d_logit_scale share [1]) from the all-gathered LSE vectors -- mvn_clip_loss_bwd."""
+    L = lib()
+    g = _req(g, "grad_output")
+    wsb = L.mvn_clip_loss_workspace_bytes(n, N, D)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=e1.device)
+    d1 = torch.empty_like(e1); d2 = torch.empty_like(e2)
+    dls = torch.empty(1, dtype=torch.float32, device=e1.device)
+    check(L.mvn_clip_loss_bwd(_p(e1), _p(e2), _p(e1_all), _p(e2_all), n, N, D, off, _p(ls), _p(lb), _p(lse_all[0]), _p(lse_all[1]), _p(g),
+                              _p(d1), _p(d2), _p(dls), _p(ws), wsb, prec, _stream()), "clip_loss_bwd")
+    _count(5)
+    return d1, d2, dls
+
+
 class ClipLossFn(torch.autograd.Function):
+    """Symmetric InfoNCE over the GLOBAL batch.  Host logic = the exchange protocol of DESIGN.md section 5 (all-gather
+    embeddings -> rank-local LSEs -> all-gather LSEs / all-reduce the loss share); the arithmetic is the two kernels
+    above.  (tests/test_dp_gloo.py drives this protocol on two CPU processes with the oracle standing in for the kernels.)"""
+
     @staticmethod
     def forward(ctx, e1, e2, logit_scale, logit_bias, prec: int):
-        L = lib()
-        e1 = _req(e1, "embs1"); e2 = _req(e2, "embs2")
-        ls = _req(logit_scale.reshape(1), "logit_scale"); lb = _req(logit_bias.reshape(1), "logit_bias")
         if e1.shape != e2.shape or e1.dim() != 2:
             raise ValueError(f"clip_loss: embeddings must both be (N, D), got {tuple(e1.shape)} and {tuple(e2.shape)}")
+        e1 = e1.contiguous(); e2 = e2.contiguous()
+        ls = logit_scale.reshape(1); lb = logit_bias.reshape(1)
         n, D = e1.shape
         grp = _DP_GROUP
         if grp is not None:
@@ -554,16 +585,10 @@ class ClipLossFn(torch.autograd.Function):
         else:
             rank, world, e1_all, e2_all = 0, 1, e1, e2
         N, off = n * world, rank * n
-        wsb = L.mvn_clip_loss_workspace_bytes(n, N, D)
-        ws = torch.empty(wsb, dtype=torch.uint8, device=e1.device)
-        loss = torch.empty(1, dtype=torch.float32, device=e1.device)
-        lse = torch.empty(2, n, dtype=torch.float32, device=e1.device)
-        check(L.mvn_clip_loss_fwd(_p(e1), _p(e2), _p(e1_all), _p(e2_all), n, N, D, off, _p(ls), _p(lb), _p(loss), _p(lse[0]), _p(lse[1]),
-                                  _p(ws), wsb, prec, _stream()), "clip_loss_fwd")
-        _count(4)
+        loss, lse = _clip_fwd_local(e1, e2, e1_all, e2_all, n, N, D, off, ls, lb, prec)
         if grp is not None:
             import torch.distributed as dist
-            lse_all = _all_gather_rows(lse.t().contiguous(), grp).t().contiguous()      # (2, N)
+            lse_all = _all_gather_rows(lse.t().contiguous(), grp).t().contiguous()      # (2, N), rank-major = global row order
             dist.all_reduce(loss, group=grp)
         else:
             lse_all = lse
@@ -573,18 +598,11 @@ class ClipLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        L = lib()
         e1, e2, e1_all, e2_all, ls, lb, lse_all = ctx.saved_tensors
         n, N, D, off, prec, ls_shape, lb_shape = ctx.meta
-        g = _req(g.reshape(1), "grad_output")
-        wsb = L.mvn_clip_loss_workspace_bytes(n, N, D)
-        ws = torch.empty(wsb, dtype=torch.uint8, device=e1.device)
-        d1 = torch.empty_like(e1); d2 = torch.empty_like(e2)
-        dls = torch.empty(1, dtype=torch.float32, device=e1.device)
-        check(L.mvn_clip_loss_bwd(_p(e1), _p(e2), _p(e1_all), _p(e2_all), n, N, D, off, _p(ls), _p(lb), _p(lse_all[0]), _p(lse_all[1]), _p(g),
-                                  _p(d1), _p(d2), _p(dls), _p(ws), wsb, prec, _stream()), "clip_loss_bwd")
-        _count(5)
-        # d loss / d logit_bias is identically zero under the two softmaxes; autograd still reports a zero tensor
+        d1, d2, dls = _clip_bwd_local(e1, e2, e1_all, e2_all, n, N, D, off, ls, lb, lse_all, g.reshape(1).contiguous(), prec)
+        # d loss / d logit_bias is identically zero under the two softmaxes; autograd still reports a zero tensor.
+        # d_logit_scale is this rank's share: it is summed over ranks by the flat gradient all-reduce like every parameter grad.
         dlb = torch.zeros(lb_shape, dtype=torch.float32, device=e1.device)
         return d1, d2, dls.reshape(ls_shape), dlb, None
 
