@@ -568,7 +568,7 @@ def _clip_bwd_local(e1, e2, e1_all, e2_all, n, N, D, off, ls, lb, lse_all, g, pr
 class ClipLossFn(torch.autograd.Function):
     """Symmetric InfoNCE over the GLOBAL batch.  Host logic = the exchange protocol of DESIGN.md section 5 (all-gather
     embeddings -> rank-local LSEs -> all-gather LSEs / all-reduce the loss share); the arithmetic is the two kernels
-    above.  (tests/test_dp_gloo.py drives this protocol on two CPU processes with the oracle standing in for the kernels.)"""
+    above.  (tests/test_dp_gloo.py drives this protocol on two CPU processes with test-side torch stand-ins for the two kernels.)"""
 
     @staticmethod
     def forward(ctx, e1, e2, logit_scale, logit_bias, prec: int):
