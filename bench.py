@@ -205,6 +205,7 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"                      # NCCL's version banner goes to stdout otherwise (ONE JSON line)
         dist.init_process_group("nccl", device_id=dev)
         ops.set_data_parallel_group(dist.group.WORLD)
     L = _lib.lib()

@@ -13,7 +13,7 @@
 //     input-gradient GEMMs, rounded to nearest TF32);
 //   * warps 2-5: epilogue -- tcgen05.ld gives every thread one output row (32 columns at a time), so LayerNorm
 //     statistics need no shuffles; tiles go through a small per-warp shared-memory transpose so that every global
-//     load/store of C, the residual, xhat ... is a full 128-byte line.
+//     load/store of C, the residual, xhat ... is a full 128-byte line (TMA loads in, TMA stores out).
 #include <mutex>
 #include <unordered_map>
 
@@ -85,22 +85,22 @@ namespace {
 using namespace tc;
 
 constexpr int TILE_M = 128;
-constexpr int STAGE_BYTES = TILE_M * 128;        // one [128 x 32 fp32] K-chunk of A
-constexpr int NSTAGE = 8;
+constexpr int STAGE_BYTES = TILE_M * 128;        // one [128 rows x 32 fp32] box: a K-chunk of A, or a 32-column chunk of the aux tile
+constexpr int NSTAGE = 7;                        // ring slots shared between the A ring (nA) and the aux ring (nX = NSTAGE - nA)
 constexpr int MAX_B_BYTES = 65536;               // N*K*4 <= 64 KB (256x64, 64x256, 192x64 ...)
-constexpr int STG_PITCH = 36;                    // floats; 16-B aligned rows, conflict-free for 128-bit accesses
-constexpr int STG_FLOATS = 32 * STG_PITCH;
 constexpr int NUM_EPI_WARPS = 4;
-constexpr int NTHREADS = 32 * (2 + NUM_EPI_WARPS);
+constexpr int EPI_WARP0 = 3;                     // warps 0,1,2 = A producer, MMA issuer, aux producer
+constexpr int NTHREADS = 32 * (EPI_WARP0 + NUM_EPI_WARPS);
 constexpr int TMEM_COLS = 512;
 
 // dynamic shared memory carve-up (byte offsets from the 1024-aligned base)
 constexpr int OFF_A = 0;
-constexpr int OFF_B = OFF_A + NSTAGE * STAGE_BYTES;                 // 131072
-constexpr int OFF_STG = OFF_B + MAX_B_BYTES;                        // 196608
-constexpr int OFF_VEC = OFF_STG + NUM_EPI_WARPS * STG_FLOATS * 4;   // bias[256] gamma[64] beta[64]
+constexpr int OFF_B = OFF_A + NSTAGE * STAGE_BYTES;                 // 114688
+constexpr int WBOX_BYTES = 32 * 128;                                // one epilogue warp's [32 rows x 32 fp32] output box
+constexpr int OFF_OUT = OFF_B + MAX_B_BYTES;                        // 180224: 4 warps x 2 boxes (TMA-store sources)
+constexpr int OFF_VEC = OFF_OUT + 2 * STAGE_BYTES;                  // bias[256] gamma[64] beta[64]
 constexpr int OFF_BAR = OFF_VEC + (256 + 64 + 64) * 4;
-constexpr int NUM_BARS = 2 * NSTAGE + 4;
+constexpr int NUM_BARS = 4 * NSTAGE + 4;
 constexpr int OFF_TMEMPTR = OFF_BAR + NUM_BARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEMPTR + 16 + 1024;                 // + slack for the manual 1024-B alignment
 
@@ -108,48 +108,50 @@ struct TcArgs {
     const float* B; float* C;
     const int32_t* n_rows_dev;
     int M_cap, N, K, b_is_nk;
+    int nA, nX;                  // ring split; nX == 0: no aux tile
     GemmEpilogue ep;
 };
 
-// coalesced [32 rows x 32 cols] block of a row-major [*, ld] matrix -> staging (row pitch STG_PITCH)
-__device__ __forceinline__ void stage_load(float* stg, const float* __restrict__ src, int row0, int rows, int ld, int c0, int lane) {
-    const int cq = (lane & 7) * 4, rr = lane >> 3;
+// this thread's row `r` (0..127) -> a [128 x 32 fp32] 128B-swizzled box (the layout TMA expects for a SWIZZLE_128B store)
+__device__ __forceinline__ void box_row_write(uint8_t* box, int r, const float* v) {
+    float4* p = reinterpret_cast<float4*>(box + r * 128);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) p[j ^ (r & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+// partial tile: the warp's [32 x 32] box -> global with a row predicate, 128-byte coalesced
+__device__ __forceinline__ void box_store_rows(const uint8_t* box, float* __restrict__ dst, int row0, int rows, int ld, int c0, int ncol, int lane) {
+    const int cq = lane & 7, rr = lane >> 3;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int r = rr + 4 * i;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row0 + r < rows) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)(row0 + r) * ld + c0 + cq));
-        *reinterpret_cast<float4*>(stg + r * STG_PITCH + cq) = v;
+        if (row0 + r < rows && cq * 4 < ncol)
+            *reinterpret_cast<float4*>(dst + (size_t)(row0 + r) * ld + c0 + cq * 4) = *reinterpret_cast<const float4*>(box + r * 128 + ((cq ^ (r & 7)) << 4));
     }
 }
-__device__ __forceinline__ void stage_store(const float* stg, float* __restrict__ dst, int row0, int rows, int ld, int c0, int lane) {
-    const int cq = (lane & 7) * 4, rr = lane >> 3;
+// row `r` (0..127) of a TMA-written [128 x 32 fp32] 128B-swizzled box -> 32 registers (conflict-free: the 8 lanes of a
+// quarter-warp hit 8 different 16-byte chunks)
+__device__ __forceinline__ void box_row_read(const uint8_t* box, int r, float* v) {
+    const float4* p = reinterpret_cast<const float4*>(box + r * 128);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int r = rr + 4 * i;
-        if (row0 + r < rows) *reinterpret_cast<float4*>(dst + (size_t)(row0 + r) * ld + c0 + cq) = *reinterpret_cast<const float4*>(stg + r * STG_PITCH + cq);
+    for (int j = 0; j < 8; ++j) {
+        const float4 t = p[j ^ (r & 7)];
+        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
     }
-}
-__device__ __forceinline__ void row_read(const float* stg, int lane, float* v) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(stg + lane * STG_PITCH + j);
-        v[j] = t.x; v[j + 1] = t.y; v[j + 2] = t.z; v[j + 3] = t.w;
-    }
-}
-__device__ __forceinline__ void row_write(float* stg, int lane, const float* v) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(stg + lane * STG_PITCH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
 }
 
 // LN_CH: 0 = plain epilogue; 1 or 2 = residual+LayerNorm epilogue over N = 32*LN_CH columns.
+// The aux tile (residual `addend` or ReLU-mask source `act_src`, same [M,N] shape as C) is streamed by its own TMA producer
+// into the aux ring, so its HBM latency is hidden exactly like the A operand's.
 template <int LN_CH>
-__global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const TcArgs a) {
+__global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapX,
+                                                              const __grid_constant__ CUtensorMap tmapC, const __grid_constant__ CUtensorMap tmapH,
+                                                              const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int N = a.N, K = a.K, KC = K >> 5;
+    const int N = a.N, K = a.K, KC = K >> 5, XC = (N + 31) >> 5;
+    const int nA = a.nA, nX = a.nX;
     const int rows = a.n_rows_dev ? min(*a.n_rows_dev, a.M_cap) : a.M_cap;
     const int ntiles = (rows + TILE_M - 1) / TILE_M;
 
@@ -158,14 +160,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
     const uint32_t bar0 = sbase + OFF_BAR;
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
-    auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * NSTAGE + b); };
-    auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * NSTAGE + 2 + b); };
+    auto xfull_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + s); };
+    auto xempty_bar = [&](int s) { return bar0 + 8u * (3 * NSTAGE + s); };
+    auto tfull_bar = [&](int b) { return bar0 + 8u * (4 * NSTAGE + b); };
+    auto tempty_bar = [&](int b) { return bar0 + 8u * (4 * NSTAGE + 2 + b); };
     volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEMPTR);
 
     // ---- one-time setup ------------------------------------------------------------------------------
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmapA);
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        if (nX) tma_prefetch_desc(&tmapX);
+        tma_prefetch_desc(&tmapC);
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1);
+            mbar_init(xfull_bar(s), 1); mbar_init(xempty_bar(s), NUM_EPI_WARPS);
+        }
         for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), NUM_EPI_WARPS); }
         fence_barrier_init();
     }
@@ -195,15 +204,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer: A operand =====
         if (lane == 0) {
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int kc = 0; kc < KC; ++kc, ++it) {
-                    const int s = it % NSTAGE;
-                    mbar_wait(empty_bar(s), ((it / NSTAGE) & 1) ^ 1);
+                    const int s = it % nA;
+                    mbar_wait(empty_bar(s), ((it / nA) & 1) ^ 1);
                     mbar_expect_tx(full_bar(s), STAGE_BYTES);
                     tma_load_2d(sbase + OFF_A + s * STAGE_BYTES, &tmapA, full_bar(s), kc * 32, tile * TILE_M);
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===== TMA producer: aux tile (residual / mask source), consumed by the epilogue warps =====
+        if (lane == 0 && nX) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int xc = 0; xc < XC; ++xc, ++it) {
+                    const int s = it % nX;
+                    mbar_wait(xempty_bar(s), ((it / nX) & 1) ^ 1);
+                    mbar_expect_tx(xfull_bar(s), STAGE_BYTES);
+                    tma_load_2d(sbase + OFF_A + (nA + s) * STAGE_BYTES, &tmapX, xfull_bar(s), xc * 32, tile * TILE_M);
                 }
             }
         }
@@ -218,8 +240,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * 256;
                 for (int kc = 0; kc < KC; ++kc, ++it) {
-                    const int s = it % NSTAGE;
-                    mbar_wait(full_bar(s), (it / NSTAGE) & 1);
+                    const int s = it % nA;
+                    mbar_wait(full_bar(s), (it / nA) & 1);
                     tc_fence_after();
                     const uint32_t a_addr = sbase + OFF_A + s * STAGE_BYTES;
                     const uint32_t b_addr = sbase + OFF_B + kc * N * 128;
@@ -235,15 +257,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
     } else {
         // ===== epilogue warps: TMEM lanes 32*(warp%4) .. +31 =====
         const int quad = warp & 3;
-        float* stg = reinterpret_cast<float*>(smem + OFF_STG) + (warp - 2) * STG_FLOATS;
         const GemmEpilogue& ep = a.ep;
-        uint32_t tc_i = 0;
+        uint32_t tc_i = 0, xit = 0, oit = 0;
+        // next aux chunk of this tile: this thread's row -> r[32]; releases the slot once the whole warp has read it
+        auto aux_row = [&](float* r) {
+            const int s = xit % nX;
+            mbar_wait(xfull_bar(s), (xit / nX) & 1);
+            box_row_read(smem + OFF_A + (nA + s) * STAGE_BYTES, quad * 32 + lane, r);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(xempty_bar(s));
+            ++xit;
+        };
+        // One 32-column chunk of this warp's 32 output rows: the lanes write their rows into one of the warp's two private
+        // [32 x 32 fp32] swizzled boxes, then lane 0 issues a TMA store of the box (full tiles) or the warp stores the rows
+        // with a predicate (the last, partial tile).  No cross-warp synchronisation: each warp owns its bulk groups.
+        uint8_t* mybox = smem + OFF_OUT + (warp - EPI_WARP0) * 2 * WBOX_BYTES;
+        auto put_chunk = [&](const CUtensorMap* tmap, float* gdst, const float* v, int tile, int c0, bool full_tile) {
+            uint8_t* box = mybox + (oit & 1) * WBOX_BYTES;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the store issued from this box two chunks ago has read it
+            __syncwarp();
+            box_row_write(box, lane, v);
+            fence_proxy_async();
+            __syncwarp();
+            if (full_tile) {
+                if (lane == 0) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 ::"l"(tmap), "r"(smem_u32(box)), "r"(c0), "r"(tile * TILE_M + quad * 32) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            } else {
+                box_store_rows(box, gdst, tile * TILE_M + quad * 32, rows, N, c0, N - c0, lane);
+            }
+            ++oit;
+        };
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tc_i) {
             const int buf = tc_i & 1;
             mbar_wait(tfull_bar(buf), (tc_i >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + buf * 256 + ((uint32_t)(quad * 32) << 16);
             const int row0 = tile * TILE_M + quad * 32;
+            const bool full_tile = tile * TILE_M + TILE_M <= rows;
             if constexpr (LN_CH == 0) {
                 for (int c0 = 0; c0 < N; c0 += 32) {
                     float v[32];
@@ -255,16 +308,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
                     } else {
                         tmem_ld32(taddr + c0, v);
                     }
-                    const int nc = half ? 16 : 32;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] += vec[(c0 + j) & 255];
                     if (ep.addend) {
                         float r[32];
-                        __syncwarp();
-                        if (!half) stage_load(stg, ep.addend, row0, rows, N, c0, lane);
-                        else if ((lane & 7) < 4) stage_load(stg, ep.addend, row0, rows, N, c0, lane);
-                        __syncwarp();
-                        row_read(stg, lane, r);
+                        aux_row(r);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] += r[j];
                     }
@@ -277,11 +325,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
                     }
                     if (ep.dact) {
                         float r[32];
-                        __syncwarp();
-                        if (!half) stage_load(stg, ep.act_src, row0, rows, N, c0, lane);
-                        else if ((lane & 7) < 4) stage_load(stg, ep.act_src, row0, rows, N, c0, lane);
-                        __syncwarp();
-                        row_read(stg, lane, r);
+                        aux_row(r);
                         if (ep.dact == 1) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] = r[j] > 0.f ? v[j] : 0.f;
@@ -290,12 +334,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
                             for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_grad(r[j]);
                         }
                     }
-                    __syncwarp();
-                    row_write(stg, lane, v);
-                    __syncwarp();
-                    if (!half) stage_store(stg, a.C, row0, rows, N, c0, lane);
-                    else if ((lane & 7) < 4) stage_store(stg, a.C, row0, rows, N, c0, lane);
-                    (void)nc;
+                    put_chunk(&tmapC, a.C, v, tile, c0, full_tile);
                 }
             } else {
                 float v[LN_CH][32];
@@ -306,10 +345,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
                     for (int j = 0; j < 32; ++j) v[c][j] += vec[c * 32 + j];
                     if (ep.addend) {
                         float r[32];
-                        __syncwarp();
-                        stage_load(stg, ep.addend, row0, rows, N, c * 32, lane);
-                        __syncwarp();
-                        row_read(stg, lane, r);
+                        aux_row(r);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[c][j] += r[j];
                     }
@@ -332,18 +368,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
                 for (int c = 0; c < LN_CH; ++c) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[c][j] *= rs;
-                    if (ep.xhat) {
-                        __syncwarp();
-                        row_write(stg, lane, v[c]);
-                        __syncwarp();
-                        stage_store(stg, ep.xhat, row0, rows, N, c * 32, lane);
-                    }
+                    if (ep.xhat) put_chunk(&tmapH, ep.xhat, v[c], tile, c * 32, full_tile);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[c][j] = fmaf(v[c][j], vec[256 + c * 32 + j], vec[320 + c * 32 + j]);
-                    __syncwarp();
-                    row_write(stg, lane, v[c]);
-                    __syncwarp();
-                    stage_store(stg, a.C, row0, rows, N, c * 32, lane);
+                    put_chunk(&tmapC, a.C, v[c], tile, c * 32, full_tile);
                 }
             }
             // this warp has drained its TMEM lanes of accumulator `buf`
@@ -351,6 +379,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(buf));
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the last TMA store's reads
     }
 
     // ---- teardown ------------------------------------------------------------------------------------------
@@ -361,7 +390,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
 }
 
 template <int LN_CH>
-int launch_tc(const CUtensorMap& tm, const TcArgs& a, cudaStream_t st) {
+int launch_tc(const CUtensorMap& tm, const CUtensorMap& tx, const CUtensorMap& tcm, const CUtensorMap& thm, const TcArgs& a, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         MVN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<LN_CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -369,11 +398,10 @@ int launch_tc(const CUtensorMap& tm, const TcArgs& a, cudaStream_t st) {
     }
     const int tiles = cdiv(a.M_cap, TILE_M);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    tc_gemm_kernel<LN_CH><<<grid, NTHREADS, SMEM_BYTES, st>>>(tm, a);
+    tc_gemm_kernel<LN_CH><<<grid, NTHREADS, SMEM_BYTES, st>>>(tm, tx, tcm, thm, a);
     MVN_LAUNCH_CHECK();
     return 0;
 }
-
 
 // ==========================================================================================================
 // Weight-gradient GEMM on tcgen05:  dW[N,K] = dY^T X,  db[N] = colsum(dY)   (contraction over the token stream).
@@ -537,16 +565,32 @@ int launch_gemm_tc(const float* A, const float* Bm, float* C, const int32_t* n_r
     if (M_cap < TILE_M) return MVN_E_UNSUPPORTED;          // tiny heads: not worth a persistent launch
     const bool ln = ep.gamma != nullptr;
     if (ln && !(N == 32 || N == 64)) return MVN_E_UNSUPPORTED;
+    if (ep.addend && ep.dact) return MVN_E_UNSUPPORTED;    // one aux stream per launch
     if (!aligned16(A) || !aligned16(C) || !aligned16(Bm) || (ep.addend && !aligned16(ep.addend)) || (ep.act_src && !aligned16(ep.act_src)) ||
         (ep.xhat && !aligned16(ep.xhat)))
         return MVN_E_UNSUPPORTED;
     if (ln) MVN_CHECK_ARG(ep.beta != nullptr, "gemm+LN: beta missing");
     const CUtensorMap* tm = get_tmap_2d(A, M_cap, K, TILE_M, false);
     if (!tm) return MVN_E_BADARG;
+    const float* aux = ep.addend ? ep.addend : (ep.dact ? ep.act_src : nullptr);
+    const CUtensorMap* tx = tm;
     TcArgs a;
     a.B = Bm; a.C = C; a.n_rows_dev = n_rows_dev; a.M_cap = M_cap; a.N = N; a.K = K; a.b_is_nk = b_is_nk ? 1 : 0; a.ep = ep;
-    if (!ln) return launch_tc<0>(*tm, a, st);
-    return N == 32 ? launch_tc<1>(*tm, a, st) : launch_tc<2>(*tm, a, st);
+    a.nA = NSTAGE; a.nX = 0;
+    if (aux) {
+        tx = get_tmap_2d(aux, M_cap, N, TILE_M, false);
+        if (!tx) return MVN_E_BADARG;
+        // split the 8 ring slots in proportion to the bytes each stream moves per tile (at least 2 each)
+        const int kc = K / 32, xc = (N + 31) / 32;
+        int nx = (NSTAGE * xc + (kc + xc) / 2) / (kc + xc);
+        nx = nx < 2 ? 2 : (nx > NSTAGE - 2 ? NSTAGE - 2 : nx);
+        a.nX = nx; a.nA = NSTAGE - nx;
+    }
+    const CUtensorMap* tcm = get_tmap_2d(C, M_cap, N, 32, false);                    // per-warp [32 x 32] store boxes
+    const CUtensorMap* thm = (ln && ep.xhat) ? get_tmap_2d(ep.xhat, M_cap, N, 32, false) : tcm;
+    if (!tcm || !thm) return MVN_E_BADARG;
+    if (!ln) return launch_tc<0>(*tm, *tx, *tcm, *thm, a, st);
+    return N == 32 ? launch_tc<1>(*tm, *tx, *tcm, *thm, a, st) : launch_tc<2>(*tm, *tx, *tcm, *thm, a, st);
 }
 
 }  // namespace mvn
