@@ -21,15 +21,21 @@ constexpr int CH = 256;                       // keys (or queries) staged in sha
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 
-__device__ __forceinline__ float tf32r(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+// Round-to-nearest TF32 without touching the XU pipe (cvt.rna.tf32 issues there, next to the exp2 the softmax needs):
+// the MMA ignores the low 13 mantissa bits of its operands, so adding half an ulp of TF32 to the bit pattern and letting
+// the hardware truncate rounds to nearest (ties away from zero).  One integer add on the ALU pipe.
+__device__ __forceinline__ float tf32r(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+// 2^x on the SFU, flush-to-zero: one MUFU.EX2 (exp2f() wraps it in a denormal-range rescale the softmax does not need;
+// ex2(-inf) = +0, which is what masked / padded positions rely on)
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 // D(16x8) += A(16x8, row) * B(8x8, col);  fragment layouts (g = lane/4, t = lane%4):
 //   a0:(g,t) a1:(g+8,t) a2:(g,t+4) a3:(g+8,t+4) ; b0:(k=t,n=g) b1:(k=t+4,n=g) ; c0:(g,2t) c1:(g,2t+1) c2:(g+8,2t) c3:(g+8,2t+1)
 __device__ __forceinline__ void mma_tf32(float* c, const float* a, float b0, float b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
                    "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
@@ -116,9 +122,14 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_fwd_mma_kernel(const float* 
                         for (int ks = 0; ks < HD / 8; ++ks)
                             mma_tf32(s[j], qa[ks], Ks[(key0 + g) * LD + ks * 8 + t], Ks[(key0 + g) * LD + ks * 8 + t + 4]);
                     }
-                    const int kc = key0 + 2 * t;
-                    if (kc >= kn) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
-                    if (kc + 1 >= kn) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+                }
+                if (kb + 64 > kn) {                      // only the last block of a sequence has keys to mask
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int kc = kb + j * 8 + 2 * t;
+                        if (kc >= kn) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+                        if (kc + 1 >= kn) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+                    }
                 }
                 float bm_lo = -INFINITY, bm_hi = -INFINITY;
 #pragma unroll
@@ -128,7 +139,7 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_fwd_mma_kernel(const float* 
                 }
                 bm_lo = quad_max(bm_lo); bm_hi = quad_max(bm_hi);          // finite: key kb < kn is always live
                 const float mn_lo = fmaxf(m_lo, bm_lo), mn_hi = fmaxf(m_hi, bm_hi);
-                const float c_lo = exp2f(m_lo - mn_lo), c_hi = exp2f(m_hi - mn_hi);
+                const float c_lo = ex2(m_lo - mn_lo), c_hi = ex2(m_hi - mn_hi);
                 m_lo = mn_lo; m_hi = mn_hi;
                 l_lo *= c_lo; l_hi *= c_hi;
 #pragma unroll
@@ -137,8 +148,8 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_fwd_mma_kernel(const float* 
                 for (int j = 0; j < 8; ++j) {
                     const int key0 = kb + j * 8;
                     if (key0 >= kn) break;
-                    const float p0 = exp2f(s[j][0] - mn_lo), p1 = exp2f(s[j][1] - mn_lo);
-                    const float p2 = exp2f(s[j][2] - mn_hi), p3 = exp2f(s[j][3] - mn_hi);
+                    const float p0 = ex2(s[j][0] - mn_lo), p1 = ex2(s[j][1] - mn_lo);
+                    const float p2 = ex2(s[j][2] - mn_hi), p3 = ex2(s[j][3] - mn_hi);
                     l_lo += p0 + p1; l_hi += p2 + p3;
                     const float pa[4] = {tf32r(p0), tf32r(p2), tf32r(p1), tf32r(p3)};      // k=t <-> key 2t, k=t+4 <-> key 2t+1
 #pragma unroll
@@ -225,10 +236,10 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
                     mma_tf32(s, qa[ks], As[(key0 + g) * LD + ks * 8 + t], As[(key0 + g) * LD + ks * 8 + t + 4]);
                     mma_tf32(dp, ga[ks], Bs[(key0 + g) * LD + ks * 8 + t], Bs[(key0 + g) * LD + ks * 8 + t + 4]);
                 }
-                const int kc = key0 + 2 * t;
-                const bool v0 = kc < kn, v1 = kc + 1 < kn;
-                const float p0 = v0 ? exp2f(s[0] - L_lo) : 0.f, p1 = v1 ? exp2f(s[1] - L_lo) : 0.f;
-                const float p2 = v0 ? exp2f(s[2] - L_hi) : 0.f, p3 = v1 ? exp2f(s[3] - L_hi) : 0.f;
+                // no key mask needed: rows of K past the sequence end are zero-filled in shared memory, so whatever (finite) dS
+                // they get multiplies a zero row in the dQ MMA below
+                const float p0 = ex2(s[0] - L_lo), p1 = ex2(s[1] - L_lo);
+                const float p2 = ex2(s[2] - L_hi), p3 = ex2(s[3] - L_hi);
                 const float da[4] = {tf32r(p0 * (dp[0] - D_lo)), tf32r(p2 * (dp[2] - D_hi)), tf32r(p1 * (dp[1] - D_lo)), tf32r(p3 * (dp[3] - D_hi))};
 #pragma unroll
                 for (int nt = 0; nt < HD / 8; ++nt)
@@ -288,7 +299,7 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
                 }
                 const int qc = qq + 2 * t;
                 const float L0 = lse_s[qc], L1 = lse_s[qc + 1], D0 = D_s[qc], D1 = D_s[qc + 1];
-                const float p0 = exp2f(s[0] - L0), p1 = exp2f(s[1] - L1), p2 = exp2f(s[2] - L0), p3 = exp2f(s[3] - L1);   // 0 on padding (L=+inf)
+                const float p0 = ex2(s[0] - L0), p1 = ex2(s[1] - L1), p2 = ex2(s[2] - L0), p3 = ex2(s[3] - L1);   // 0 on padding (L=+inf)
                 const float pa[4] = {tf32r(p0), tf32r(p2), tf32r(p1), tf32r(p3)};
                 const float da[4] = {tf32r(p0 * (dp[0] - D0)), tf32r(p2 * (dp[2] - D0)), tf32r(p1 * (dp[1] - D1)), tf32r(p3 * (dp[3] - D1))};
 #pragma unroll
