@@ -369,7 +369,8 @@ def main():
     ap.add_argument("--workload", default="c4", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=1024, help="samples per GPU per step")
     ap.add_argument("--ref-batch", type=int, default=64, help="samples per CPU reference step (bounded sample)")
-    ap.add_argument("--dropout", type=float, default=0.0)
+    ap.add_argument("--dropout", type=float, default=0.00021844858312997214,
+                    help="transformer dropout p (default: pretrain_config/maven_pretrain_config.yaml); the CPU reference arm uses 0")
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
                     help="tf32: tcgen05/mma tensor-core tier (fp32 storage, fp32 accumulate; parity 1e-3); fp32: FFMA tier (parity 1e-5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -128,6 +128,15 @@ int mvn_unpack_rows(const float* X, const int32_t* tok_src, const uint8_t* keyva
 int mvn_pack_rows(const float* dense, const int32_t* tok_src, const uint8_t* keyvalid, const int32_t* n_rows_dev,
                   int BT, int E, float* X, void* stream);
 
+/* A6, agg="attn": nn.MultiheadAttention(E, H) with one learnable query per sequence over the zero-padded tokens, no key
+ * mask.  src/transformer_utils.py:241-247.  q[E] = in_proj(query) (shared by all sequences), kv[B*T,2E] = k|v after
+ * in_proj (padded rows therefore carry the biases, as in the reference); score scale 1/sqrt(E/H).
+ * fwd writes out[B,E] (heads concatenated, before out_proj) and probs[B,H,T]; bwd writes dkv[B*T,2E] and dq[E]
+ * (summed over the batch); workspace >= B*E floats. */
+int mvn_query_pool_fwd(const float* q, const float* kv, int B, int T, int E, int H, float* out, float* probs, void* stream);
+int mvn_query_pool_bwd(const float* q, const float* kv, const float* probs, const float* dout, int B, int T, int E, int H,
+                       float* dkv, float* dq, void* workspace, size_t workspace_bytes, void* stream);
+
 /* A7: x / ||x||_2 per row, no epsilon.  src/models_multimodal.py:279,286,293. */
 int mvn_l2norm_fwd(const float* X, float* Y, float* norm, int B, int D, void* stream);
 int mvn_l2norm_bwd(const float* dY, const float* Y, const float* norm, float* dX, int B, int D, void* stream);
@@ -148,8 +157,9 @@ typedef struct {
     int32_t prec;         /* 0 fp32, 1 tf32 tensor cores                            */
     int32_t ff_mult;      /* 4 (Transformer default, src/transformer_utils.py:124)  */
     float   ln_eps;       /* 1e-5                                                   */
-    float   dropout_p;    /* 0 for parity; >0 uses a counter-based in-kernel mask   */
-    uint64_t seed;        /* dropout seed (ignored when dropout_p==0)               */
+    float   dropout_p;    /* nn.Dropout p of Transformer/TransformerBlock (0 = off); counter-based in-kernel mask,
+                             regenerated (not stored) by the backward from the same seed */
+    uint64_t seed;        /* dropout seed of THIS call (ignored when dropout_p==0)  */
 } mvn_seq_cfg;
 
 size_t mvn_seq_param_count(const mvn_seq_cfg* cfg);
@@ -159,6 +169,11 @@ int mvn_seq_encoder_fwd(const mvn_seq_cfg* cfg, const float* params, const float
                         void* workspace, size_t workspace_bytes, void* stream);
 int mvn_seq_encoder_bwd(const mvn_seq_cfg* cfg, const float* params, const float* x, const float* dout,
                         float* grads, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The keep/scale factor (0 or 1/(1-p)) mvn_seq_encoder_* applies at dropout site `site` to element [row, col] of the
+ * packed [rows, cols] activation: site 0 = transformer input, 1+2l / 2+2l = after norm1 / norm2 of layer l
+ * (src/transformer_utils.py:147,112,115).  Lets a caller reproduce or test a dropped-out forward exactly. */
+int mvn_dropout_scale(uint64_t seed, int site, float p, int rows, int cols, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * A10/A11: symmetric InfoNCE, streamed; the N x N logits are never written.  src/loss.py:14-38.

@@ -49,8 +49,11 @@ _SIGS = {
     "mvn_pool_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P, P]),
     "mvn_unpack_rows": (c_int, [P, P, P, P, c_int, c_int, P, P]),
     "mvn_pack_rows": (c_int, [P, P, P, P, c_int, c_int, P, P]),
+    "mvn_query_pool_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, P]),
+    "mvn_query_pool_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, c_size_t, P]),
     "mvn_l2norm_fwd": (c_int, [P, P, P, c_int, c_int, P]),
     "mvn_l2norm_bwd": (c_int, [P, P, P, P, c_int, c_int, P]),
+    "mvn_dropout_scale": (c_int, [c_uint64, c_int, c_float, c_int, c_int, P, P]),
     "mvn_seq_param_count": (c_size_t, [POINTER(SeqCfg)]),
     "mvn_seq_workspace_bytes": (c_size_t, [POINTER(SeqCfg)]),
     "mvn_seq_encoder_fwd": (c_int, [POINTER(SeqCfg), P, P, P, P, P, P, P, c_size_t, P]),

@@ -101,6 +101,37 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
     return cdf + x * pdf;
 }
 
+// ---- dropout (nn.Dropout in Transformer / TransformerBlock, src/transformer_utils.py:112,115,147) ---------------------
+// Counter-based: the keep/drop decision of element `idx` at dropout site `site` is a pure function of (seed, site, idx),
+// so the backward regenerates the forward's mask instead of storing it.  thresh == 0 switches it off.
+struct DropCfg {
+    uint32_t thresh = 0;     // P(drop) = thresh / 2^32
+    float scale = 1.0f;      // 1 / (1 - p) on kept elements
+    uint32_t s0 = 0, s1 = 0; // seed words (already mixed with the site id)
+};
+// Two-level hash: a strong per-row key (computed once per row) and a cheap per-element mix of (rowkey, col).
+__device__ __forceinline__ uint32_t drop_rowkey(const DropCfg& d, uint32_t row) {
+    uint32_t h = row ^ d.s0;
+    h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+    return h ^ d.s1;
+}
+__device__ __forceinline__ float drop_scale(const DropCfg& d, uint32_t rowkey, uint32_t col) {
+    uint32_t h = rowkey + col * 0x9E3779B1u;
+    h ^= h >> 15; h *= 0x2c1b3c6du; h ^= h >> 12; h *= 0x297a2d39u; h ^= h >> 15;
+    return h >= d.thresh ? d.scale : 0.f;
+}
+static inline DropCfg make_drop(float p, uint64_t seed, uint32_t site) {
+    DropCfg d;
+    if (!(p > 0.f)) return d;
+    const double t = (double)p * 4294967296.0;
+    d.thresh = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
+    if (d.thresh == 0) d.thresh = 1;
+    d.scale = 1.0f / (1.0f - p);
+    d.s0 = (uint32_t)seed ^ (site * 0x85EBCA77u + 0x165667B1u);
+    d.s1 = (uint32_t)(seed >> 32) ^ (site * 0xC2B2AE3Du);
+    return d;
+}
+
 // ---- internal launchers shared between the per-op C entry points and the fused encoder -------------
 struct GemmEpilogue {
     const float* bias = nullptr;     // [N]
@@ -114,6 +145,7 @@ struct GemmEpilogue {
     float* xhat = nullptr;
     float* rstd = nullptr;
     float eps = 1e-5f;
+    DropCfg drop;                    // applied to Y after the LayerNorm affine (xhat stays pre-dropout)
 };
 // C[M,N] = A[M,K] * op(B):  b_is_nk: B stored [N,K] (nn.Linear weight) else B stored [K,N].
 int launch_gemm(const float* A, const float* Bm, float* C, const int32_t* n_rows_dev, int M_cap, int N, int K,
@@ -125,8 +157,12 @@ int launch_wgrad_partials(const float* dY, const float* X, const int32_t* n_rows
 int launch_reduce_partials(const float* partial, size_t pstride, size_t n, float* out, int accumulate, cudaStream_t st);
 int launch_ln_bwd(const float* dY, const float* xhat, const float* rstd, const float* gamma, float* dZ,
                   const int32_t* n_rows_dev, int M_cap, int E, float* partial, size_t pstride, size_t goff, size_t boff,
-                  cudaStream_t st);
+                  cudaStream_t st, const DropCfg& drop = DropCfg());     // drop: dY is the gradient AFTER the dropout that followed this LayerNorm
 int launch_embed_bwd_partials(const float* x, const int32_t* tok_src, const float* dout, const int32_t* n_rows_dev,
-                              int M_cap, int T, int E, int nband, float* partial, size_t pstride, size_t off, cudaStream_t st);
+                              int M_cap, int T, int E, int nband, float* partial, size_t pstride, size_t off, cudaStream_t st,
+                              const DropCfg& drop = DropCfg());
+int launch_embed_fwd(const float* x, const float* t, const int32_t* cu_seqlens, const int32_t* tok_src, const float* div_term,
+                     const float* w, const float* b, const float* band_emb, int B, int T, int E, int nband, float* out,
+                     cudaStream_t st, const DropCfg& drop);
 
 }  // namespace mvn

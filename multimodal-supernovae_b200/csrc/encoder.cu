@@ -125,7 +125,7 @@ int check_cfg(const mvn_seq_cfg* c) {
     MVN_UNSUPPORTED(c->nband <= 4 && c->T % c->nband == 0, "seq_encoder: nband=%d must be <=4 and divide T=%d", c->nband, c->T);
     MVN_UNSUPPORTED(c->agg == MVN_AGG_MEAN || c->agg == MVN_AGG_MAX || c->agg == MVN_AGG_NONE, "seq_encoder: agg=%d unsupported", c->agg);
     MVN_UNSUPPORTED(c->ff_mult >= 1 && c->ff_mult <= 8, "seq_encoder: ff_mult=%d unsupported", c->ff_mult);
-    MVN_UNSUPPORTED(c->dropout_p == 0.0f, "seq_encoder: in-kernel dropout not built yet (dropout_p=%g)", (double)c->dropout_p);
+    MVN_CHECK_ARG(c->dropout_p >= 0.0f && c->dropout_p < 1.0f, "seq_encoder: dropout_p=%g outside [0,1)", (double)c->dropout_p);
     if (c->agg != MVN_AGG_NONE) MVN_CHECK_ARG(c->n_out > 0 && c->enc_dim >= 0, "seq_encoder: n_out must be positive, enc_dim >= 0");
     return 0;
 }
@@ -161,8 +161,9 @@ extern "C" int mvn_seq_encoder_fwd(const mvn_seq_cfg* cfg, const float* params, 
     const float scale = 1.0f / sqrtf((float)E);
 
     MVN_TRY(mvn_pack_plan(mask, c.B, c.T, 1, w.cu, w.tok_src, w.keyvalid, st));
-    MVN_TRY(mvn_embed_fwd(x, t, w.cu, w.tok_src, div_term, params + o.emb_w, params + o.emb_b, c.nband > 1 ? params + o.band : nullptr,
-                          c.B, c.T, E, c.nband, w.x0, st));
+    // dropout sites (src/transformer_utils.py:147,112,115): 0 = transformer input, 1+2l = after norm1, 2+2l = after norm2 of layer l
+    MVN_TRY(launch_embed_fwd(x, t, w.cu, w.tok_src, div_term, params + o.emb_w, params + o.emb_b, c.nband > 1 ? params + o.band : nullptr,
+                             c.B, c.T, E, c.nband, w.x0, st, make_drop(c.dropout_p, c.seed, 0)));
     const float* xin = w.x0;
     for (int l = 0; l < c.depth; ++l) {
         const float* P = params + o.layer0 + (size_t)l * o.layer_stride;
@@ -172,12 +173,14 @@ extern "C" int mvn_seq_encoder_fwd(const mvn_seq_cfg* cfg, const float* params, 
         MVN_TRY(mvn_attention_fwd(lb.qkv, w.cu, nullptr, lb.att, lb.lse, c.B, E, c.H, scale, c.prec, st));
         GemmEpilogue e1;
         e1.bias = P + o.bu; e1.addend = xin; e1.gamma = P + o.g1; e1.beta = P + o.b1n; e1.xhat = lb.xhat1; e1.rstd = lb.rstd1; e1.eps = c.ln_eps;
+        e1.drop = make_drop(c.dropout_p, c.seed, 1 + 2 * l);
         MVN_TRY(launch_gemm(lb.att, P + o.wu, lb.x1, nrows, M, E, E, true, e1, c.prec, st));
         GemmEpilogue e2;
         e2.bias = P + o.b1; e2.act = MVN_ACT_RELU;
         MVN_TRY(launch_gemm(lb.x1, P + o.w1, lb.h, nrows, M, F, E, true, e2, c.prec, st));
         GemmEpilogue e3;
         e3.bias = P + o.b2; e3.addend = lb.x1; e3.gamma = P + o.g2; e3.beta = P + o.b2n; e3.xhat = lb.xhat2; e3.rstd = lb.rstd2; e3.eps = c.ln_eps;
+        e3.drop = make_drop(c.dropout_p, c.seed, 2 + 2 * l);
         MVN_TRY(launch_gemm(lb.h, P + o.w2, lb.x2, nrows, M, E, F, true, e3, c.prec, st));
         xin = lb.x2;
     }
@@ -252,7 +255,7 @@ extern "C" int mvn_seq_encoder_bwd(const mvn_seq_cfg* cfg, const float* params, 
         const LayerBuf lb = w.layer(l);
         const float* xin = l > 0 ? w.layer(l - 1).x2 : w.x0;
         // norm2 backward: dX (grad of x2) -> dz2 in w.dz
-        MVN_TRY(launch_ln_bwd(w.dX, lb.xhat2, lb.rstd2, P + o.g2, w.dz, nrows, M, E, part, ps, o.g2, o.b2n, st));
+        MVN_TRY(launch_ln_bwd(w.dX, lb.xhat2, lb.rstd2, P + o.g2, w.dz, nrows, M, E, part, ps, o.g2, o.b2n, st, make_drop(c.dropout_p, c.seed, 2 + 2 * l)));
         // ff.2: dW2 = dz2^T h ; dh = (dz2 W2) * relu'(h)
         MVN_TRY(launch_wgrad_partials(w.dz, lb.h, nrows, M, E, F, part, ps, o.w2, (long long)o.b2, c.prec, st));
         GemmEpilogue eh;
@@ -264,7 +267,7 @@ extern "C" int mvn_seq_encoder_bwd(const mvn_seq_cfg* cfg, const float* params, 
         e1.addend = w.dz;
         MVN_TRY(launch_gemm(w.dh, P + o.w1, w.dA, nrows, M, E, F, false, e1, c.prec, st));
         // norm1 backward: dA -> dz1 in w.dz
-        MVN_TRY(launch_ln_bwd(w.dA, lb.xhat1, lb.rstd1, P + o.g1, w.dz, nrows, M, E, part, ps, o.g1, o.b1n, st));
+        MVN_TRY(launch_ln_bwd(w.dA, lb.xhat1, lb.rstd1, P + o.g1, w.dz, nrows, M, E, part, ps, o.g1, o.b1n, st, make_drop(c.dropout_p, c.seed, 1 + 2 * l)));
         // unifyheads: dWu = dz1^T att ; datt = dz1 Wu  (into w.dA)
         MVN_TRY(launch_wgrad_partials(w.dz, lb.att, nrows, M, E, E, part, ps, o.wu, (long long)o.bu, c.prec, st));
         GemmEpilogue e2;
@@ -278,7 +281,7 @@ extern "C" int mvn_seq_encoder_bwd(const mvn_seq_cfg* cfg, const float* params, 
         MVN_TRY(launch_reduce_partials(part, ps, o.layer_stride, grads + o.layer0 + (size_t)l * o.layer_stride, 0, st));
     }
     // embedding_mag / band_emb
-    MVN_TRY(launch_embed_bwd_partials(x, w.tok_src, w.dX, nrows, M, c.T, E, c.nband, part, ps, 0, st));
+    MVN_TRY(launch_embed_bwd_partials(x, w.tok_src, w.dX, nrows, M, c.T, E, c.nband, part, ps, 0, st, make_drop(c.dropout_p, c.seed, 0)));
     MVN_TRY(launch_reduce_partials(part, ps, (size_t)(2 + (c.nband > 1 ? c.nband : 0)) * E, grads + o.emb_w, 0, st));
     return 0;
 }

@@ -127,6 +127,10 @@ __global__ void __launch_bounds__((BM / 4) * (BN / 4)) gemm_kernel(const GemmArg
             if (live) {
                 float4 xh = make_float4(d[0] * rs, d[1] * rs, d[2] * rs, d[3] * rs);
                 float4 y = make_float4(fmaf(xh.x, g[0], be[0]), fmaf(xh.y, g[1], be[1]), fmaf(xh.z, g[2], be[2]), fmaf(xh.w, g[3], be[3]));
+                if (ep.drop.thresh) {
+                    const uint32_t rk = drop_rowkey(ep.drop, (uint32_t)m);
+                    y.x *= drop_scale(ep.drop, rk, nb); y.y *= drop_scale(ep.drop, rk, nb + 1); y.z *= drop_scale(ep.drop, rk, nb + 2); y.w *= drop_scale(ep.drop, rk, nb + 3);
+                }
                 *reinterpret_cast<float4*>(a.C + (size_t)m * N + nb) = y;
                 if (ep.xhat) *reinterpret_cast<float4*>(ep.xhat + (size_t)m * N + nb) = xh;
                 if (ep.rstd && tx == 0) ep.rstd[m] = rs;

@@ -371,6 +371,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
                     if (ep.xhat) put_chunk(&tmapH, ep.xhat, v[c], tile, c * 32, full_tile);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[c][j] = fmaf(v[c][j], vec[256 + c * 32 + j], vec[320 + c * 32 + j]);
+                    if (ep.drop.thresh) {
+                        const uint32_t rk = drop_rowkey(ep.drop, (uint32_t)(row0 + lane));
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[c][j] *= drop_scale(ep.drop, rk, (uint32_t)(c * 32 + j));
+                    }
                     put_chunk(&tmapC, a.C, v[c], tile, c * 32, full_tile);
                 }
             }

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict_
                                                         const int32_t* __restrict__ cu, const int32_t* __restrict__ tok_src,
                                                         const float* __restrict__ div_term, const float* __restrict__ w,
                                                         const float* __restrict__ bias, const float* __restrict__ band_emb,
-                                                        int B, int T, int E, int nband, float* __restrict__ out) {
+                                                        int B, int T, int E, int nband, float* __restrict__ out, const DropCfg drop) {
     const int rows = cu[B];
     const int lane = threadIdx.x & 31;
     const int per_band = T / (nband > 0 ? nband : 1);
@@ -100,11 +100,13 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict_
         const int src = tok_src[m];
         const float xv = x[src], tv = t[src];
         const int band = (nband > 1) ? min((src % T) / per_band, nband - 1) : 0;
+        const uint32_t rk = drop.thresh ? drop_rowkey(drop, (uint32_t)m) : 0u;
         for (int e = lane; e < E; e += 32) {
             const float arg = __fmul_rn(tv, div_term[e >> 1]);
             const float pe = (e & 1) ? cosf(arg) : sinf(arg);
             float v = fmaf(xv, w[e], bias[e]) + pe;
             if (nband > 1) v += band_emb[band * E + e];
+            if (drop.thresh) v *= drop_scale(drop, rk, (uint32_t)e);
             out[(size_t)m * E + e] = v;
         }
     }
@@ -114,7 +116,8 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict_
 template <int PER>
 __global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ tok_src,
                                                         const float* __restrict__ dout, const int32_t* n_rows_dev, int M_cap,
-                                                        int T, int E, int nband, float* __restrict__ partial, size_t pstride, size_t off) {
+                                                        int T, int E, int nband, float* __restrict__ partial, size_t pstride, size_t off,
+                                                        const DropCfg drop) {
     constexpr int MAXB = 4;
     __shared__ float red[8][(2 + MAXB) * 32 * PER];
     const int rows = n_rows_dev ? min(*n_rows_dev, M_cap) : M_cap;
@@ -129,10 +132,12 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict_
         const int src = tok_src[m];
         const float xv = x[src];
         const int band = (nband > 1) ? min((src % T) / per_band, nband - 1) : 0;
+        const uint32_t rk = drop.thresh ? drop_rowkey(drop, (uint32_t)m) : 0u;
 #pragma unroll
         for (int p = 0; p < PER; ++p) {
             const int e = lane + 32 * p;
-            const float g = e < E ? dout[(size_t)m * E + e] : 0.f;
+            float g = e < E ? dout[(size_t)m * E + e] : 0.f;
+            if (drop.thresh) g *= drop_scale(drop, rk, (uint32_t)e);
             dw[p] = fmaf(g, xv, dw[p]);
             db[p] += g;
 #pragma unroll
@@ -166,7 +171,8 @@ template <int PER>
 __global__ void __launch_bounds__(LNB_WARPS * 32) ln_bwd_kernel(const float* __restrict__ dY, const float* __restrict__ xhat,
                                                                 const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                                 float* __restrict__ dZ, const int32_t* n_rows_dev, int M_cap, int E,
-                                                                float* __restrict__ partial, size_t pstride, size_t goff, size_t boff) {
+                                                                float* __restrict__ partial, size_t pstride, size_t goff, size_t boff,
+                                                                const DropCfg drop) {
     __shared__ float red[LNB_WARPS][2 * 32 * PER];
     const int rows = n_rows_dev ? min(*n_rows_dev, M_cap) : M_cap;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -183,10 +189,12 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) ln_bwd_kernel(const float* __r
             const int m = m0 + u * stride;
             const bool live = m < rows;
             rs[u] = live ? rstd[m] : 0.f;
+            const uint32_t rk = drop.thresh ? drop_rowkey(drop, (uint32_t)m) : 0u;
 #pragma unroll
             for (int p = 0; p < PER; ++p) {
                 const int e = lane + 32 * p;
                 dy[u][p] = (live && e < E) ? dY[(size_t)m * E + e] : 0.f;
+                if (drop.thresh) dy[u][p] *= drop_scale(drop, rk, (uint32_t)e);
                 xh[u][p] = (live && e < E) ? xhat[(size_t)m * E + e] : 0.f;
             }
         }
@@ -334,38 +342,65 @@ __global__ void relu_bwd_kernel(const float* __restrict__ dy, const float* __res
 
 int launch_ln_bwd(const float* dY, const float* xhat, const float* rstd, const float* gamma, float* dZ,
                   const int32_t* n_rows_dev, int M_cap, int E, float* partial, size_t pstride, size_t goff, size_t boff,
-                  cudaStream_t st) {
+                  cudaStream_t st, const DropCfg& drop) {
     MVN_CHECK_ARG(dY && xhat && rstd && gamma && dZ && partial, "layernorm_bwd: null pointer");
     MVN_UNSUPPORTED(E >= 1 && E <= 128, "layernorm_bwd: E=%d outside [1,128]", E);
     ProfScope prof(PROF_ROW, st);
     const int per = (E + 31) / 32;
     switch (per) {
-        case 1: ln_bwd_kernel<1><<<kSlabs, LNB_WARPS * 32, 0, st>>>(dY, xhat, rstd, gamma, dZ, n_rows_dev, M_cap, E, partial, pstride, goff, boff); break;
-        case 2: ln_bwd_kernel<2><<<kSlabs, LNB_WARPS * 32, 0, st>>>(dY, xhat, rstd, gamma, dZ, n_rows_dev, M_cap, E, partial, pstride, goff, boff); break;
-        default: ln_bwd_kernel<4><<<kSlabs, LNB_WARPS * 32, 0, st>>>(dY, xhat, rstd, gamma, dZ, n_rows_dev, M_cap, E, partial, pstride, goff, boff); break;
+        case 1: ln_bwd_kernel<1><<<kSlabs, LNB_WARPS * 32, 0, st>>>(dY, xhat, rstd, gamma, dZ, n_rows_dev, M_cap, E, partial, pstride, goff, boff, drop); break;
+        case 2: ln_bwd_kernel<2><<<kSlabs, LNB_WARPS * 32, 0, st>>>(dY, xhat, rstd, gamma, dZ, n_rows_dev, M_cap, E, partial, pstride, goff, boff, drop); break;
+        default: ln_bwd_kernel<4><<<kSlabs, LNB_WARPS * 32, 0, st>>>(dY, xhat, rstd, gamma, dZ, n_rows_dev, M_cap, E, partial, pstride, goff, boff, drop); break;
     }
     MVN_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_embed_bwd_partials(const float* x, const int32_t* tok_src, const float* dout, const int32_t* n_rows_dev,
-                              int M_cap, int T, int E, int nband, float* partial, size_t pstride, size_t off, cudaStream_t st) {
+                              int M_cap, int T, int E, int nband, float* partial, size_t pstride, size_t off, cudaStream_t st,
+                              const DropCfg& drop) {
     MVN_CHECK_ARG(x && tok_src && dout && partial, "embed_bwd: null pointer");
     MVN_UNSUPPORTED(E >= 1 && E <= 128 && nband >= 1 && nband <= 4, "embed_bwd: E=%d nband=%d unsupported", E, nband);
     ProfScope prof(PROF_ROW, st);
     const int per = (E + 31) / 32;
     switch (per) {
-        case 1: embed_bwd_kernel<1><<<kSlabs, 256, 0, st>>>(x, tok_src, dout, n_rows_dev, M_cap, T, E, nband, partial, pstride, off); break;
-        case 2: embed_bwd_kernel<2><<<kSlabs, 256, 0, st>>>(x, tok_src, dout, n_rows_dev, M_cap, T, E, nband, partial, pstride, off); break;
-        default: embed_bwd_kernel<4><<<kSlabs, 256, 0, st>>>(x, tok_src, dout, n_rows_dev, M_cap, T, E, nband, partial, pstride, off); break;
+        case 1: embed_bwd_kernel<1><<<kSlabs, 256, 0, st>>>(x, tok_src, dout, n_rows_dev, M_cap, T, E, nband, partial, pstride, off, drop); break;
+        case 2: embed_bwd_kernel<2><<<kSlabs, 256, 0, st>>>(x, tok_src, dout, n_rows_dev, M_cap, T, E, nband, partial, pstride, off, drop); break;
+        default: embed_bwd_kernel<4><<<kSlabs, 256, 0, st>>>(x, tok_src, dout, n_rows_dev, M_cap, T, E, nband, partial, pstride, off, drop); break;
     }
     MVN_LAUNCH_CHECK();
     return 0;
 }
 
+int launch_embed_fwd(const float* x, const float* t, const int32_t* cu_seqlens, const int32_t* tok_src, const float* div_term,
+                     const float* w, const float* b, const float* band_emb, int B, int T, int E, int nband, float* out,
+                     cudaStream_t st, const DropCfg& drop) {
+    MVN_CHECK_ARG(x && t && cu_seqlens && tok_src && div_term && w && b && out && B > 0 && T > 0 && E > 0, "embed_fwd: bad arguments");
+    MVN_CHECK_ARG(E % 2 == 0, "embed_fwd: E must be even (sin/cos pairs), got %d", E);
+    MVN_CHECK_ARG(nband >= 1 && (nband == 1 || (band_emb && T % nband == 0)), "embed_fwd: nband=%d needs band_emb and T%%nband==0", nband);
+    const int blocks = min(cdiv(B * T, 8), num_sms() * 8);
+    ProfScope prof(PROF_ROW, st);
+    embed_fwd_kernel<<<blocks, 256, 0, st>>>(x, t, cu_seqlens, tok_src, div_term, w, b, band_emb, B, T, E, nband, out, drop);
+    MVN_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void dropout_scale_kernel(const DropCfg drop, size_t n, int cols, float* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = drop.thresh ? drop_scale(drop, drop_rowkey(drop, (uint32_t)(i / cols)), (uint32_t)(i % cols)) : 1.0f;
+}
+
 }  // namespace mvn
 
 using namespace mvn;
+
+extern "C" int mvn_dropout_scale(uint64_t seed, int site, float p, int rows, int cols, float* out, void* stream) {
+    MVN_CHECK_ARG(out && rows > 0 && cols > 0 && p >= 0.f && p < 1.f && site >= 0, "dropout_scale: bad arguments");
+    const size_t n = (size_t)rows * cols;
+    dropout_scale_kernel<<<(int)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024), 256, 0, (cudaStream_t)stream>>>(make_drop(p, seed, (uint32_t)site), n, cols, out);
+    MVN_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int mvn_pack_plan(const uint8_t* mask, int B, int T, int valid_only, int32_t* cu_seqlens, int32_t* tok_src,
                              uint8_t* keyvalid, void* stream) {
@@ -389,14 +424,7 @@ extern "C" int mvn_pack_plan(const uint8_t* mask, int B, int T, int valid_only, 
 extern "C" int mvn_embed_fwd(const float* x, const float* t, const int32_t* cu_seqlens, const int32_t* tok_src,
                              const float* div_term, const float* w, const float* b, const float* band_emb, int B, int T,
                              int E, int nband, float* out, void* stream) {
-    MVN_CHECK_ARG(x && t && cu_seqlens && tok_src && div_term && w && b && out && B > 0 && T > 0 && E > 0, "embed_fwd: bad arguments");
-    MVN_CHECK_ARG(E % 2 == 0, "embed_fwd: E must be even (sin/cos pairs), got %d", E);
-    MVN_CHECK_ARG(nband >= 1 && (nband == 1 || (band_emb && T % nband == 0)), "embed_fwd: nband=%d needs band_emb and T%%nband==0", nband);
-    const int blocks = min(cdiv(B * T, 8), num_sms() * 8);
-    ProfScope prof(PROF_ROW, (cudaStream_t)stream);
-    embed_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, t, cu_seqlens, tok_src, div_term, w, b, band_emb, B, T, E, nband, out);
-    MVN_LAUNCH_CHECK();
-    return 0;
+    return launch_embed_fwd(x, t, cu_seqlens, tok_src, div_term, w, b, band_emb, B, T, E, nband, out, (cudaStream_t)stream, DropCfg());
 }
 
 extern "C" int mvn_embed_bwd(const float* x, const int32_t* cu_seqlens, const int32_t* tok_src, const float* dout, int B, int T,

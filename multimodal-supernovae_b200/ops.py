@@ -507,9 +507,33 @@ class ConvMixerFn(torch.autograd.Function):
 
 
 class QueryPoolFn(torch.autograd.Function):
+    """agg='attn' pooling core (mvn_query_pool_fwd/_bwd): q (1,E) projected query, kv (B,T,2E) projected keys|values."""
+
     @staticmethod
-    def forward(ctx, q, kv, B, T, E, H):
-        raise NotImplementedError("maven_b200: agg='attn' pooling kernel is not built yet")
+    def forward(ctx, q, kv, B: int, T: int, E: int, H: int):
+        L = lib()
+        q2 = _req(q, "query").reshape(E)
+        kv2 = _req(kv, "kv").reshape(B * T, 2 * E)
+        out = torch.empty(B, E, dtype=torch.float32, device=kv.device)
+        probs = torch.empty(B, H, T, dtype=torch.float32, device=kv.device)
+        check(L.mvn_query_pool_fwd(_p(q2), _p(kv2), B, T, E, H, _p(out), _p(probs), _stream()), "query_pool_fwd")
+        _count(1)
+        ctx.save_for_backward(q2, kv2, probs)
+        ctx.dims = (B, T, E, H, q.shape, kv.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = lib()
+        q2, kv2, probs = ctx.saved_tensors
+        B, T, E, H, qshape, kvshape = ctx.dims
+        dout = _req(dout, "grad_output")
+        dkv = torch.empty_like(kv2)
+        dq = torch.empty(E, dtype=torch.float32, device=dout.device)
+        ws = torch.empty(B * E * 4, dtype=torch.uint8, device=dout.device)
+        check(L.mvn_query_pool_bwd(_p(q2), _p(kv2), _p(probs), _p(dout), B, T, E, H, _p(dkv), _p(dq), _p(ws), ws.numel(), _stream()), "query_pool_bwd")
+        _count(2)
+        return dq.view(qshape), dkv.view(kvshape), None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------------

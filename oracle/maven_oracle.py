@@ -73,20 +73,32 @@ def self_attention(sd: SD, p: str, x: Tensor, mask: Optional[Tensor], heads: int
 # --------------------------------------------------------------------------------------
 # A4  TransformerBlock.forward (post-norm, ReLU FFN)      src/transformer_utils.py:109-116
 # A5  Transformer.forward                                  src/transformer_utils.py:143-153
-# Dropout is the identity here: parity is defined at dropout=0 / eval.
+# Dropout (:112,:115,:147) is the identity unless the caller supplies the multiplicative keep
+# factors `drop` (0 or 1/(1-p), shape (B,T,E)) for each site -- torch's RNG stream cannot be
+# matched by a fused kernel, so dropout parity is defined on a GIVEN mask.
 # --------------------------------------------------------------------------------------
-def transformer_block(sd: SD, p: str, x: Tensor, mask: Optional[Tensor], heads: int) -> Tensor:
+def transformer_block(sd: SD, p: str, x: Tensor, mask: Optional[Tensor], heads: int,
+                      drop1: Optional[Tensor] = None, drop2: Optional[Tensor] = None) -> Tensor:
     e = x.shape[-1]
     a = self_attention(sd, p + "attention.", x, mask, heads)
     x = F.layer_norm(a + x, (e,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], 1e-5)
+    if drop1 is not None:
+        x = x * drop1
     f = F.linear(x, sd[p + "ff.0.weight"], sd[p + "ff.0.bias"])
     f = F.linear(torch.relu(f), sd[p + "ff.2.weight"], sd[p + "ff.2.bias"])
-    return F.layer_norm(f + x, (e,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], 1e-5)
+    x = F.layer_norm(f + x, (e,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], 1e-5)
+    return x if drop2 is None else x * drop2
 
 
-def transformer(sd: SD, p: str, x: Tensor, mask: Optional[Tensor], heads: int, depth: int) -> Tensor:
+def transformer(sd: SD, p: str, x: Tensor, mask: Optional[Tensor], heads: int, depth: int,
+                drop_scales: Optional[Sequence[Tensor]] = None) -> Tensor:
+    """drop_scales: 1 + 2*depth keep factors in site order [input, (norm1, norm2) per layer]."""
+    if drop_scales is not None:
+        x = x * drop_scales[0]
     for i in range(depth):
-        x = transformer_block(sd, f"{p}tblocks.{i}.", x, mask, heads)
+        d1 = None if drop_scales is None else drop_scales[1 + 2 * i]
+        d2 = None if drop_scales is None else drop_scales[2 + 2 * i]
+        x = transformer_block(sd, f"{p}tblocks.{i}.", x, mask, heads, d1, d2)
     return x
 
 
@@ -108,10 +120,11 @@ def seq_embed(sd: SD, p: str, x: Tensor, t: Tensor, emb: int, nband: int, time_n
 
 
 def seq_encoder(sd: SD, p: str, x: Tensor, t: Tensor, mask: Tensor, *, emb: int, heads: int,
-                depth: int, nband: int = 1, agg: str = "mean", time_norm: float = 10000.0) -> Tensor:
+                depth: int, nband: int = 1, agg: str = "mean", time_norm: float = 10000.0,
+                drop_scales: Optional[Sequence[Tensor]] = None) -> Tensor:
     """x (B,T,1), t (B,T), mask (B,T) bool -> (B,n_out)   [or (B,T,emb) for agg='pretraining']."""
     h = seq_embed(sd, p, x, t, emb, nband, time_norm)
-    h = transformer(sd, p + "transformer.", h, mask, heads, depth)
+    h = transformer(sd, p + "transformer.", h, mask, heads, depth, drop_scales)
     h = h * mask[:, :, None]
     if agg == "mean":
         h = h.sum(dim=1) / mask.sum(dim=1)[:, None]

@@ -1,0 +1,10 @@
+set -x
+cd $GRAFT_REPO_ROOT
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 | tee gpurun_out/r9_pytest.log
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r9_bench_tf32.json 2> gpurun_out/r9_bench.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r9_bench_tf32.json'))
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['config']['dropout'], d['roofline']['frac'], d['kernel_breakdown_ms'], d['loss_last'])
+PY
+tail -5 gpurun_out/r9_bench.err

@@ -174,7 +174,7 @@ def _load_encoder(g):
     return enc, cfg, grads
 
 
-@pytest.mark.parametrize("name", ["enc_lc_mean", "enc_sp_mean", "enc_lc_max", "enc_lc_pre"])
+@pytest.mark.parametrize("name", ["enc_lc_mean", "enc_sp_mean", "enc_lc_max", "enc_lc_pre", "enc_lc_attn"])
 def test_seq_encoder_golden(name):
     g = load_golden(name)
     enc, cfg, grads = _load_encoder(g)
@@ -414,3 +414,46 @@ def test_retrieval_ranks():
     e1, e2 = torch.randn(200, 128), torch.randn(200, 128)
     r = ops.retrieval_ranks(e1.to(dev()), e2.to(dev())).cpu()
     assert torch.equal(r.long(), O.retrieval_ranks(e1.double(), e2.double()))
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+def test_seq_encoder_dropout_given_mask(L, prec):
+    """In-kernel dropout (Transformer input + after both LayerNorms of every block): the kernels' counter-based masks are
+    read back with mvn_dropout_scale, scattered to the padded layout and injected into the oracle; forward and parameter
+    gradients must then agree like in the dropout-free case.  Also: same seed -> same output, new seed -> different."""
+    from maven_b200.transformer_utils import TransformerWithTimeEmbeddings, set_precision
+    gen = torch.Generator().manual_seed(21)
+    kw = dict(n_out=32, nband=2, agg="mean", time_norm=20583.37, emb=64, heads=8, depth=3)
+    B, T, E, p_drop, seed = 12, 200, 64, 0.2, 0x1234ABCD5678
+    x, t, m = ragged(gen, B, T, 2, 300.0, 5, 100)
+    torch.manual_seed(3)
+    enc = TransformerWithTimeEmbeddings(dropout=p_drop, **kw)
+    sdg = {k: v.detach().float().requires_grad_() for k, v in enc.state_dict().items()}
+    enc = set_precision(enc.to(dev()).train(), prec)
+    enc.dropout_seed = seed
+    y = enc(x[..., None].to(dev()), t.to(dev()), m.to(dev()))
+    w = torch.randn(y.shape, generator=gen)
+    (y * w.to(dev())).sum().backward()
+    y2 = enc(x[..., None].to(dev()), t.to(dev()), m.to(dev()))
+    assert torch.equal(y, y2)
+    enc.dropout_seed = seed + 1
+    assert not torch.equal(y, enc(x[..., None].to(dev()), t.to(dev()), m.to(dev())))
+    # the masks the kernels used, packed rows -> padded (B,T,E)
+    M = int(m.sum())
+    pos = torch.nonzero(m.flatten()).flatten()
+    scales = []
+    for site in range(1 + 2 * kw["depth"]):
+        buf = torch.empty(M, E, device=dev())
+        assert L.mvn_dropout_scale(seed, site, p_drop, M, E, P(buf), S()) == 0
+        full = torch.ones(B * T, E)
+        full[pos] = buf.cpu()
+        scales.append(full.view(B, T, E))
+    keep = torch.stack([s_[m] for s_ in scales]).ne(0).float().mean().item()
+    assert abs(keep - (1 - p_drop)) < 0.01                      # keep rate ~ 1-p
+    okw = {k: kw[k] for k in ("emb", "heads", "depth", "nband", "agg", "time_norm")}
+    yr = O.seq_encoder(sdg, "", x[..., None], t, m, drop_scales=scales, **okw)
+    (yr * w).sum().backward()
+    tol_f, tol_g = (2 * TOL, 1e-3) if prec == "fp32" else (1e-3, 3e-2)     # tf32 gradient noise is amplified by the 1/(1-p) rescale
+    assert relerr(y, yr) < tol_f
+    for k, p_ in enc.named_parameters():
+        assert relerr(p_.grad, sdg[k].grad) < tol_g, k
