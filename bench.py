@@ -108,33 +108,79 @@ def flops_per_step(wl, batch):
 
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region: NVML in a background thread (nvidia_ml_py), falling
+    back to an `nvidia-smi -lms` child process when NVML is not importable."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, period_s=0.05):
+        self.index, self.period, self.rows, self.proc, self.thread, self.stop_flag = index, period_s, [], None, None, False
+        self.max_mhz, self.mode = None, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            phys = index_of_visible(self.index)
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            R = pynvml
+            bits = {"hw_slowdown": R.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": R.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": R.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": R.nvmlClocksThrottleReasonSwPowerCap}
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        self.rows.append((mhz, [n for n, b in bits.items() if rs & b]))
+                    except Exception:
+                        pass
+                    time.sleep(self.period)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            self.mode = "nvml"
+            return
+        except Exception:
+            pass
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            self.mode = "nvidia-smi"
         except Exception:
             self.proc = None
 
     def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            r = [c.strip() for c in line.split(",")]
+            if r and r[0].isdigit():
+                if len(r) > 1 and r[1].isdigit():
+                    self.max_mhz = max(self.max_mhz or 0, int(r[1]))
+                self.rows.append((int(r[0]), [n for i, n in enumerate(names) if len(r) > 3 + i and r[3 + i].lower().startswith("active")]))
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = max([int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()] or [0])
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
+        if self.proc is not None:
+            self.proc.terminate()
+        if self.mode is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = sorted({n for r in self.rows for n in r[1]})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm), "source": self.mode}
+
+
+def index_of_visible(local_index):
+    """NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list."""
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        parts = [p.strip() for p in vis.split(",") if p.strip()]
+        if local_index < len(parts) and parts[local_index].isdigit():
+            return int(parts[local_index])
+    return local_index
 
 
 def peaks():
@@ -242,24 +288,28 @@ def run_gpu(args):
         step(resident)
     sync()
 
-    # one profiled step with every class timed -> kernel-class breakdown and the dominant class
+    # ---- per-class device timing: K steps with every kernel class bracketed by CUDA events on the launching stream ---------
+    # (kept out of the throughput region below: event records between launches would defeat the programmatic dependent
+    # launches that overlap each tensor-core kernel's prologue with its predecessor's tail)
     names = ["gemm", "wgrad", "attn_fwd", "attn_bwd", "row", "loss", "optim", "conv"]
     L.mvn_prof_enable(0xFF)
-    step(resident)
+    for _ in range(args.steps):
+        flush.fill_(1)
+        step(resident)
     torch.cuda.synchronize()
-    breakdown = {}
+    breakdown, prof_tot = {}, {}
     for c, nme in enumerate(names):
         ms, cnt = ctypes.c_double(), ctypes.c_longlong()
         L.mvn_prof_read(c, ctypes.byref(ms), ctypes.byref(cnt))
-        breakdown[nme] = {"ms": round(ms.value, 4), "launches": cnt.value}
+        breakdown[nme] = {"ms": round(ms.value / args.steps, 4), "launches": cnt.value // args.steps}
+        prof_tot[nme] = (ms.value, cnt.value)
     L.mvn_prof_enable(0)
     top = max(("gemm", "wgrad", "attn_fwd", "attn_bwd", "row"), key=lambda k: breakdown[k]["ms"])
-    top_id = names.index(top)
+    ms_t, cnt_t = ctypes.c_double(prof_tot[top][0]), ctypes.c_longlong(prof_tot[top][1])
 
     # ---- timed region: K steps, device-resident inputs, per-step CUDA events, L2 flushed between steps ----
     sampler = ClockSampler(local)
     sampler.start()
-    L.mvn_prof_enable(1 << top_id)
     launches0 = L.mvn_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sync()
@@ -272,24 +322,23 @@ def run_gpu(args):
     sync()
     wall = time.perf_counter() - wall0
     launches = L.mvn_launch_count() - launches0
-    ms_t, cnt_t = ctypes.c_double(), ctypes.c_longlong()
-    L.mvn_prof_read(top_id, ctypes.byref(ms_t), ctypes.byref(cnt_t))
-    L.mvn_prof_enable(0)
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    clocks = sampler.stop()            # sampled during the throughput region only: NVML queries perturb the sync-per-step e2e loop
 
     # ---- e2e: pinned host batch -> H2D -> step -> D2H loss, everything inside the timed region -----------
+    def e2e_step():
+        batch = [None if v is None else v.to(dev, non_blocking=True) for v in pinned]
+        return step(batch).item()                              # device->host read of the step's loss
+
+    for _ in range(2):                                         # settle the allocator for the per-step input buffers
+        e2e_step()
     sync()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
-    e0.record()
     last = None
     for _ in range(args.steps):
-        batch = [None if v is None else v.to(dev, non_blocking=True) for v in pinned]
-        last = step(batch).item()                              # device->host read of the step's loss
-    e1.record()
+        last = e2e_step()
     sync()
     e2e_wall = time.perf_counter() - t0
-    clocks = sampler.stop()
 
     t = torch.tensor([dev_ms, e2e_wall * 1e3, float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -343,6 +392,7 @@ def run_gpu(args):
         "roofline": {"bound": "hbm" if hbm_bound else "tensor", "kernel_class": top, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
                      "traffic": traffic, "algorithmic_per_launch": per_launch, "avg_launch_ms": avg_ms, "peak_source": src,
                      "launches_timed": cnt_t.value, "class_ms_per_step": ms_t.value / args.steps,
+                     "timing": f"CUDA events around every launch of the class over {args.steps} steps run right before the throughput region",
                      "accounting": "class average over its launches in the timed region; executed work (valid tokens only); "
                                    "padded-equivalent step FLOPs in flops_per_step.padded_train"},
         "kernel_classes": classes,

@@ -1,5 +1,6 @@
 // Error channel and device queries of the C ABI.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -21,6 +22,11 @@ int num_sms() {
         else return 148;
     }
     return cached;
+}
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MVN_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
 }
 static long long g_launches = 0;
 void note_launch() { ++g_launches; }

@@ -80,6 +80,7 @@ __device__ __forceinline__ void load_afrag(float (*a)[4], const float* __restric
 template <int HD>
 __global__ void __launch_bounds__(ATC_THREADS) attn_fwd_mma_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ cu,
                                                                    float* __restrict__ out, float* __restrict__ lse, int E, int H, float scale) {
+    pdl_trigger();
     constexpr int LD = HD + 4;
     __shared__ __align__(16) float Ks[CH * LD];
     __shared__ __align__(16) float Vs[CH * LD];
@@ -179,6 +180,7 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
                                                                    const float* __restrict__ out, const float* __restrict__ lse,
                                                                    const float* __restrict__ dout, float* __restrict__ dqkv,
                                                                    int E, int H, float scale) {
+    pdl_trigger();
     constexpr int LD = HD + 4;
     __shared__ __align__(16) float As[CH * LD];     // phase 1: K        phase 2: Q
     __shared__ __align__(16) float Bs[CH * LD];     // phase 1: V        phase 2: dO

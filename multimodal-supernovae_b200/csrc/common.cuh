@@ -101,6 +101,15 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
     return cdf + x * pdf;
 }
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------------
+// Every heavy kernel calls pdl_trigger() first thing: once all of its CTAs have started, a dependent kernel launched
+// with the programmatic-serialization attribute may take over SMs as they drain and run its prologue (barrier init,
+// TMEM allocation, weight staging) under this kernel's tail.  Such a dependent must call pdl_wait() before it touches
+// anything its predecessor wrote.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();      // env MVN_PDL=0 switches the attribute off (A/B measurements)
+
 // ---- dropout (nn.Dropout in Transformer / TransformerBlock, src/transformer_utils.py:112,115,147) ---------------------
 // Counter-based: the keep/drop decision of element `idx` at dropout site `site` is a pure function of (seed, site, idx),
 // so the backward regenerates the forward's mask instead of storing it.  thresh == 0 switches it off.

@@ -235,6 +235,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ dY
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, size_t pstride, size_t n,
                                                               int nslabs, float* __restrict__ out, int accumulate) {
     __shared__ float red[8][33];
+    pdl_trigger();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t i = (size_t)blockIdx.x * 32 + lane;
     float acc = 0.f;

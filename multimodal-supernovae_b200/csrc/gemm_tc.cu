@@ -147,14 +147,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
                                                               const __grid_constant__ CUtensorMap tmapC, const __grid_constant__ CUtensorMap tmapH,
                                                               const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
+    pdl_trigger();
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int N = a.N, K = a.K, KC = K >> 5, XC = (N + 31) >> 5;
     const int nA = a.nA, nX = a.nX;
-    const int rows = a.n_rows_dev ? min(*a.n_rows_dev, a.M_cap) : a.M_cap;
-    const int ntiles = (rows + TILE_M - 1) / TILE_M;
-
     float* Bs = reinterpret_cast<float*>(smem + OFF_B);
     float* vec = reinterpret_cast<float*>(smem + OFF_VEC);
     const uint32_t bar0 = sbase + OFF_BAR;
@@ -179,18 +177,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(sbase + OFF_TMEMPTR, TMEM_COLS);
-    // weights -> swizzled K-major smem: element (n,k) lives in block kc=k/32 at sw128_off(n, k%32); rounded to TF32
-    if (a.b_is_nk) {                 // B[n][k], k contiguous
-        for (int idx = threadIdx.x; idx < N * (K >> 2); idx += NTHREADS) {
-            const int n = idx / (K >> 2), k = (idx % (K >> 2)) << 2;
-            const float4 w = __ldg(reinterpret_cast<const float4*>(a.B + (size_t)n * K + k));
-            const float4 t = make_float4(to_tf32(w.x), to_tf32(w.y), to_tf32(w.z), to_tf32(w.w));
-            *reinterpret_cast<float4*>(Bs + (size_t)(k >> 5) * N * 32 + sw128_off(n, k & 31)) = t;
-        }
-    } else {                         // B[k][n], n contiguous: transpose while staging
-        for (int idx = threadIdx.x; idx < K * N; idx += NTHREADS) {
-            const int k = idx / N, n = idx % N;
-            Bs[(size_t)(k >> 5) * N * 32 + sw128_off(n, k & 31)] = to_tf32(__ldg(a.B + idx));
+    // weights -> swizzled K-major smem: element (n,k) lives in block kc=k/32 at sw128_off(n, k%32); rounded to TF32.
+    // 128-bit loads, 8 independent loads in flight per thread (this prologue is pure L2 latency).
+    {
+        constexpr int UN = 8;
+        const int nvec = (N * K) >> 2;
+        for (int i0 = threadIdx.x; i0 < nvec; i0 += NTHREADS * UN) {
+            float4 w[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int i = i0 + u * NTHREADS;
+                w[u] = i < nvec ? __ldg(reinterpret_cast<const float4*>(a.B) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int i = i0 + u * NTHREADS;
+                if (i >= nvec) break;
+                if (a.b_is_nk) {         // B[n][k], k contiguous: 4 consecutive k of one row n -> one 16-byte chunk
+                    const int n = i / (K >> 2), k = (i % (K >> 2)) << 2;
+                    *reinterpret_cast<float4*>(Bs + (size_t)(k >> 5) * N * 32 + sw128_off(n, k & 31)) =
+                        make_float4(to_tf32(w[u].x), to_tf32(w[u].y), to_tf32(w[u].z), to_tf32(w[u].w));
+                } else {                 // B[k][n], n contiguous: transpose while staging (4 rows n of one column k)
+                    const int k = i / (N >> 2), n = (i % (N >> 2)) << 2;
+                    float* dst = Bs + (size_t)(k >> 5) * N * 32;
+                    dst[sw128_off(n, k & 31)] = to_tf32(w[u].x);
+                    dst[sw128_off(n + 1, k & 31)] = to_tf32(w[u].y);
+                    dst[sw128_off(n + 2, k & 31)] = to_tf32(w[u].z);
+                    dst[sw128_off(n + 3, k & 31)] = to_tf32(w[u].w);
+                }
+            }
         }
     }
     for (int i = threadIdx.x; i < N; i += NTHREADS) vec[i] = a.ep.bias ? a.ep.bias[i] : 0.f;
@@ -202,6 +217,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // Everything above reads only parameters (weights, bias, LayerNorm affine); from here on the kernel consumes what
+    // its predecessor in the stream produced.
+    pdl_wait();
+    const int rows = a.n_rows_dev ? min(*a.n_rows_dev, a.M_cap) : a.M_cap;
+    const int ntiles = (rows + TILE_M - 1) / TILE_M;
 
     if (warp == 0) {
         // ===== TMA producer: A operand =====
@@ -403,7 +423,13 @@ int launch_tc(const CUtensorMap& tm, const CUtensorMap& tx, const CUtensorMap& t
     }
     const int tiles = cdiv(a.M_cap, TILE_M);
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    tc_gemm_kernel<LN_CH><<<grid, NTHREADS, SMEM_BYTES, st>>>(tm, tx, tcm, thm, a);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    MVN_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<LN_CH>, tm, tx, tcm, thm, a));
     MVN_LAUNCH_CHECK();
     return 0;
 }
@@ -438,6 +464,7 @@ struct WgArgs {
 __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapY, const __grid_constant__ CUtensorMap tmapX,
                                                                  const WgArgs a) {
     extern __shared__ uint8_t smem_raw[];
+    pdl_trigger();
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -446,8 +473,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
     const int MB = (N + 127) >> 7;                            // 128-row accumulator blocks
     const int stage_bytes = (NB + KB) * WG_BOX;
     const int nstage = min(WG_MAXSTAGE, WG_RING / stage_bytes);
-    const int rows = a.n_rows_dev ? min(*a.n_rows_dev, a.M_cap) : a.M_cap;
-    const int ntiles = (rows + WG_TOK - 1) / WG_TOK;
     const int bias_col = MB * K;
 
     const uint32_t bar0 = sbase + WG_OFF_BAR;
@@ -470,6 +495,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();                                   // prologue above touched no activation; now consume the predecessor's output
+    const int rows = a.n_rows_dev ? min(*a.n_rows_dev, a.M_cap) : a.M_cap;
+    const int ntiles = (rows + WG_TOK - 1) / WG_TOK;
     const bool have_work = (int)blockIdx.x < ntiles;
 
     if (warp == 0) {
@@ -616,7 +644,13 @@ int launch_wgrad_tc(const float* dY, const float* X, const int32_t* n_rows_dev, 
     }
     WgArgs a;
     a.n_rows_dev = n_rows_dev; a.M_cap = M_cap; a.N = N; a.K = K; a.partial = partial; a.pstride = pstride; a.woff = woff; a.boff = boff;
-    tc_wgrad_kernel<<<kSlabs, WG_THREADS, WG_SMEM, st>>>(*ty, *tx, a);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kSlabs); cfg.blockDim = dim3(WG_THREADS); cfg.dynamicSmemBytes = WG_SMEM; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    MVN_CUDA(cudaLaunchKernelEx(&cfg, tc_wgrad_kernel, *ty, *tx, a));
     MVN_LAUNCH_CHECK();
     return 0;
 }

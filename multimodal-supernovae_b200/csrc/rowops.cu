@@ -113,13 +113,15 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict_
 }
 
 // partial[s][off + e] = sum dout*x ; [off+E+e] = sum dout ; [off+2E + band*E + e] = sum dout over band
+// 16 warps per CTA, 4 rows in flight per warp (index -> x -> dout is a dependent chain: latency, not bytes, bounds it).
+constexpr int EMB_WARPS = 16;
 template <int PER>
-__global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ tok_src,
-                                                        const float* __restrict__ dout, const int32_t* n_rows_dev, int M_cap,
-                                                        int T, int E, int nband, float* __restrict__ partial, size_t pstride, size_t off,
-                                                        const DropCfg drop) {
-    constexpr int MAXB = 4;
-    __shared__ float red[8][(2 + MAXB) * 32 * PER];
+__global__ void __launch_bounds__(EMB_WARPS * 32) embed_bwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ tok_src,
+                                                                   const float* __restrict__ dout, const int32_t* n_rows_dev, int M_cap,
+                                                                   int T, int E, int nband, float* __restrict__ partial, size_t pstride, size_t off,
+                                                                   const DropCfg drop) {
+    constexpr int MAXB = 4, U = 4;
+    __shared__ float red[EMB_WARPS][(2 + MAXB) * 32 * PER];
     const int rows = n_rows_dev ? min(*n_rows_dev, M_cap) : M_cap;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int per_band = T / (nband > 0 ? nband : 1);
@@ -128,20 +130,32 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict_
     for (int p = 0; p < PER; ++p) { dw[p] = 0.f; db[p] = 0.f;
 #pragma unroll
         for (int k = 0; k < MAXB; ++k) dbd[k][p] = 0.f; }
-    for (int m = blockIdx.x * 8 + wid; m < rows; m += gridDim.x * 8) {
-        const int src = tok_src[m];
-        const float xv = x[src];
-        const int band = (nband > 1) ? min((src % T) / per_band, nband - 1) : 0;
-        const uint32_t rk = drop.thresh ? drop_rowkey(drop, (uint32_t)m) : 0u;
+    const int stride = gridDim.x * EMB_WARPS;
+    for (int m0 = blockIdx.x * EMB_WARPS + wid; m0 < rows; m0 += U * stride) {
+        int src[U]; float xv[U]; float g[U][PER];
 #pragma unroll
-        for (int p = 0; p < PER; ++p) {
-            const int e = lane + 32 * p;
-            float g = e < E ? dout[(size_t)m * E + e] : 0.f;
-            if (drop.thresh) g *= drop_scale(drop, rk, (uint32_t)e);
-            dw[p] = fmaf(g, xv, dw[p]);
-            db[p] += g;
+        for (int u = 0; u < U; ++u) { const int m = m0 + u * stride; src[u] = m < rows ? tok_src[m] : 0; }
 #pragma unroll
-            for (int k = 0; k < MAXB; ++k) dbd[k][p] += (k == band) ? g : 0.f;
+        for (int u = 0; u < U; ++u) {
+            const int m = m0 + u * stride;
+            xv[u] = m < rows ? x[src[u]] : 0.f;
+#pragma unroll
+            for (int p = 0; p < PER; ++p) { const int e = lane + 32 * p; g[u][p] = (m < rows && e < E) ? dout[(size_t)m * E + e] : 0.f; }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int m = m0 + u * stride;
+            const int band = (nband > 1) ? min((src[u] % T) / per_band, nband - 1) : 0;
+            const uint32_t rk = drop.thresh ? drop_rowkey(drop, (uint32_t)m) : 0u;
+#pragma unroll
+            for (int p = 0; p < PER; ++p) {
+                float gv = g[u][p];
+                if (drop.thresh) gv *= drop_scale(drop, rk, (uint32_t)(lane + 32 * p));
+                dw[p] = fmaf(gv, xv[u], dw[p]);
+                db[p] += gv;
+#pragma unroll
+                for (int k = 0; k < MAXB; ++k) dbd[k][p] += (k == band) ? gv : 0.f;
+            }
         }
     }
 #pragma unroll
@@ -159,7 +173,7 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict_
         if (e >= E) continue;
         float s = 0.f;
 #pragma unroll
-        for (int w8 = 0; w8 < 8; ++w8) s += red[w8][i];
+        for (int w8 = 0; w8 < EMB_WARPS; ++w8) s += red[w8][i];
         pp[(size_t)sec * E + e] = s;
     }
 }
@@ -174,6 +188,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) ln_bwd_kernel(const float* __r
                                                                 float* __restrict__ partial, size_t pstride, size_t goff, size_t boff,
                                                                 const DropCfg drop) {
     __shared__ float red[LNB_WARPS][2 * 32 * PER];
+    pdl_trigger();
     const int rows = n_rows_dev ? min(*n_rows_dev, M_cap) : M_cap;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float gam[PER], dg[PER], dbt[PER];
@@ -364,9 +379,9 @@ int launch_embed_bwd_partials(const float* x, const int32_t* tok_src, const floa
     ProfScope prof(PROF_ROW, st);
     const int per = (E + 31) / 32;
     switch (per) {
-        case 1: embed_bwd_kernel<1><<<kSlabs, 256, 0, st>>>(x, tok_src, dout, n_rows_dev, M_cap, T, E, nband, partial, pstride, off, drop); break;
-        case 2: embed_bwd_kernel<2><<<kSlabs, 256, 0, st>>>(x, tok_src, dout, n_rows_dev, M_cap, T, E, nband, partial, pstride, off, drop); break;
-        default: embed_bwd_kernel<4><<<kSlabs, 256, 0, st>>>(x, tok_src, dout, n_rows_dev, M_cap, T, E, nband, partial, pstride, off, drop); break;
+        case 1: embed_bwd_kernel<1><<<kSlabs, EMB_WARPS * 32, 0, st>>>(x, tok_src, dout, n_rows_dev, M_cap, T, E, nband, partial, pstride, off, drop); break;
+        case 2: embed_bwd_kernel<2><<<kSlabs, EMB_WARPS * 32, 0, st>>>(x, tok_src, dout, n_rows_dev, M_cap, T, E, nband, partial, pstride, off, drop); break;
+        default: embed_bwd_kernel<4><<<kSlabs, EMB_WARPS * 32, 0, st>>>(x, tok_src, dout, n_rows_dev, M_cap, T, E, nband, partial, pstride, off, drop); break;
     }
     MVN_LAUNCH_CHECK();
     return 0;

@@ -69,6 +69,8 @@ def gemms(M, E, prec):
         dw = torch.empty(N, K, device=dev); db = torch.empty(N, device=dev)
         ms = timeit(lambda: L.mvn_linear_bwd_weight(P(dy), P(xx), P(dw), P(db), None, M, N, K, 0, P(ws), wsb, prec, S()))
         report(f"{nm:12s} [{tag}]", ms, M * 4 * (N + K), 2 * M * N * K)
+        ms = timeit(lambda: L.mvn_linear_bwd_weight(P(dy), P(xx), P(dw), None, None, M, N, K, 0, P(ws), wsb, prec, S()))
+        report(f"{nm:12s} nobias [{tag}]", ms, M * 4 * (N + K), 2 * M * N * K)
 
 
 def attention(B, T, E, H, nmin, nmax, prec):
@@ -95,6 +97,9 @@ if __name__ == "__main__":
     a = ap.parse_args()
     B = a.batch
     for prec in [int(p) for p in a.precs.split(",")]:
+        if "fixed" in a.what:              # one / two tiles per CTA: the per-launch fixed cost of the persistent kernels
+            gemms(128 * 148, 64, prec)
+            gemms(2 * 128 * 148, 64, prec)
         if "gemm" in a.what:
             gemms(B * 120, 64, prec)
             gemms(B * 165, 32, prec)

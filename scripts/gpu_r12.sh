@@ -1,0 +1,11 @@
+set -x
+cd $GRAFT_REPO_ROOT
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee gpurun_out/r12_pytest.log
+timeout 300 python scripts/bench_kernels.py --what fixed,gemm --precs 1 2>&1 | grep -v nobias | tee gpurun_out/r12_kern.log
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r12_bench_tf32.json 2> gpurun_out/r12_bench.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r12_bench_tf32.json'))
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['kernel_breakdown_ms'], d['loss_last'])
+PY
+tail -5 gpurun_out/r12_bench.err
