@@ -220,59 +220,69 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
     // Everything above reads only parameters (weights, bias, LayerNorm affine); from here on the kernel consumes what
     // its predecessor in the stream produced.
     pdl_wait();
-    const int rows = a.n_rows_dev ? min(*a.n_rows_dev, a.M_cap) : a.M_cap;
+    int rows = a.n_rows_dev ? min(__ldg(a.n_rows_dev), a.M_cap) : a.M_cap;
+    rows = __reduce_min_sync(0xffffffffu, rows);          // identical in every lane; keeps the role loops on the uniform datapath
     const int ntiles = (rows + TILE_M - 1) / TILE_M;
 
+    // The three single-warp roles below run warp-convergent loops over warp-uniform values (ring slot / phase counters, no
+    // divisions; descriptors advanced by constants) and put only the issuing instructions under elect.sync.
     if (warp == 0) {
         // ===== TMA producer: A operand =====
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int kc = 0; kc < KC; ++kc, ++it) {
-                    const int s = it % nA;
-                    mbar_wait(empty_bar(s), ((it / nA) & 1) ^ 1);
+        uint32_t s = 0, ph = 1;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int kc = 0; kc < KC; ++kc) {
+                mbar_wait(empty_bar(s), ph);
+                if (elect_one()) {
                     mbar_expect_tx(full_bar(s), STAGE_BYTES);
                     tma_load_2d(sbase + OFF_A + s * STAGE_BYTES, &tmapA, full_bar(s), kc * 32, tile * TILE_M);
                 }
+                __syncwarp();
+                if (++s == (uint32_t)nA) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 2) {
         // ===== TMA producer: aux tile (residual / mask source), consumed by the epilogue warps =====
-        if (lane == 0 && nX) {
-            uint32_t it = 0;
+        if (nX) {
+            uint32_t s = 0, ph = 1;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int xc = 0; xc < XC; ++xc, ++it) {
-                    const int s = it % nX;
-                    mbar_wait(xempty_bar(s), ((it / nX) & 1) ^ 1);
-                    mbar_expect_tx(xfull_bar(s), STAGE_BYTES);
-                    tma_load_2d(sbase + OFF_A + (nA + s) * STAGE_BYTES, &tmapX, xfull_bar(s), xc * 32, tile * TILE_M);
+                for (int xc = 0; xc < XC; ++xc) {
+                    mbar_wait(xempty_bar(s), ph);
+                    if (elect_one()) {
+                        mbar_expect_tx(xfull_bar(s), STAGE_BYTES);
+                        tma_load_2d(sbase + OFF_A + (nA + s) * STAGE_BYTES, &tmapX, xfull_bar(s), xc * 32, tile * TILE_M);
+                    }
+                    __syncwarp();
+                    if (++s == (uint32_t)nX) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc = idesc_tf32(TILE_M, N, 0, 0);
-            uint32_t it = 0, tc_i = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tc_i) {
-                const int buf = tc_i & 1;
-                mbar_wait(tempty_bar(buf), ((tc_i >> 1) & 1) ^ 1);
+        const uint32_t idesc = idesc_tf32(TILE_M, N, 0, 0);
+        const uint64_t adesc0 = smem_desc_sw128(sbase + OFF_A, 0, 1024);
+        const uint64_t bdesc0 = smem_desc_sw128(sbase + OFF_B, 0, 1024);
+        const uint32_t b_inc = (uint32_t)(N * 128) >> 4;              // next 32-wide K chunk of the staged weights
+        uint32_t s = 0, ph = 0, buf = 0, tph = 1;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            mbar_wait(tempty_bar(buf), tph);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * 256;
+            uint64_t bdesc = bdesc0;
+            for (int kc = 0; kc < KC; ++kc, bdesc += b_inc) {
+                mbar_wait(full_bar(s), ph);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * 256;
-                for (int kc = 0; kc < KC; ++kc, ++it) {
-                    const int s = it % nA;
-                    mbar_wait(full_bar(s), (it / nA) & 1);
-                    tc_fence_after();
-                    const uint32_t a_addr = sbase + OFF_A + s * STAGE_BYTES;
-                    const uint32_t b_addr = sbase + OFF_B + kc * N * 128;
+                const uint64_t adesc = adesc0 + s * (uint32_t)(STAGE_BYTES >> 4);
+                if (elect_one()) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        umma_tf32(d_tmem, smem_desc_sw128(a_addr + j * 32, 0, 1024), smem_desc_sw128(b_addr + j * 32, 0, 1024), idesc,
-                                  (kc | j) != 0);
+                    for (int j = 0; j < 4; ++j) umma_tf32(d_tmem, adesc + 2u * j, bdesc + 2u * j, idesc, (uint32_t)(kc | j));
                     umma_commit(empty_bar(s));            // frees the A stage once these MMAs have read it
                 }
-                umma_commit(tfull_bar(buf));              // accumulator complete -> epilogue
+                __syncwarp();
+                if (++s == (uint32_t)nA) { s = 0; ph ^= 1; }
             }
+            if (elect_one()) umma_commit(tfull_bar(buf));              // accumulator complete -> epilogue
+            __syncwarp();
+            if ((buf ^= 1) == 0) tph ^= 1;
         }
     } else {
         // ===== epilogue warps: TMEM lanes 32*(warp%4) .. +31 =====
@@ -445,8 +455,6 @@ int launch_tc(const CUtensorMap& tm, const CUtensorMap& tx, const CUtensorMap& t
 //   db rides along as a second tiny MMA against a constant block of ones (N=16 columns, column 0 is read back).
 // The accumulators stay in TMEM for the CTA's whole token range; each CTA writes one slab of partials
 // (deterministic: launch_reduce_partials sums the kSlabs slabs in a fixed order).
-constexpr int WG_TOK = 32;                         // tokens per pipeline stage
-constexpr int WG_BOX = WG_TOK * 128;               // bytes of one [32 tok x 32 float] box
 constexpr int WG_RING = 200 * 1024;
 constexpr int WG_OFF_ONES = WG_RING + 16 * 1024;   // slack: an M=128 A operand may over-read up to 16 KB of don't-care rows
 constexpr int WG_OFF_BAR = WG_OFF_ONES + 1024;
@@ -458,11 +466,19 @@ constexpr int WG_THREADS = 192;
 struct WgArgs {
     const int32_t* n_rows_dev;
     int M_cap, N, K;
+    int nstage;
     float* partial; size_t pstride, woff; long long boff;
 };
 
+// The producer and the MMA issuer are single-warp instruction streams on the critical path of every stage, so both
+// loops are written to stay warp-convergent with warp-uniform values (stage / phase counters instead of divisions,
+// descriptors advanced by adding constants to their low word) and only the issuing instructions sit under elect.sync:
+// ptxas then keeps the whole loop on the uniform datapath instead of broadcasting operands per instruction.
+// TOK = tokens per pipeline stage (box rows of the two tensor maps).
+template <int TOK>
 __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmapY, const __grid_constant__ CUtensorMap tmapX,
                                                                  const WgArgs a) {
+    constexpr int BOX = TOK * 128;                            // bytes of one [TOK tok x 32 float] box
     extern __shared__ uint8_t smem_raw[];
     pdl_trigger();
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -471,20 +487,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
     const int N = a.N, K = a.K;
     const int NB = N >> 5, KB = K >> 5;                       // 32-wide boxes of dY and X per stage
     const int MB = (N + 127) >> 7;                            // 128-row accumulator blocks
-    const int stage_bytes = (NB + KB) * WG_BOX;
-    const int nstage = min(WG_MAXSTAGE, WG_RING / stage_bytes);
+    const uint32_t stage_bytes = (uint32_t)(NB + KB) * BOX;
+    const uint32_t nstage = (uint32_t)a.nstage;
     const int bias_col = MB * K;
 
     const uint32_t bar0 = sbase + WG_OFF_BAR;
-    auto full_bar = [&](int s) { return bar0 + 8u * s; };
-    auto empty_bar = [&](int s) { return bar0 + 8u * (WG_MAXSTAGE + s); };
+    const uint32_t full0 = bar0, empty0 = bar0 + 8u * WG_MAXSTAGE;
     const uint32_t done_bar = bar0 + 8u * (2 * WG_MAXSTAGE);
     volatile uint32_t* tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + WG_OFF_TMEMPTR);
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmapY);
         tma_prefetch_desc(&tmapX);
-        for (int s = 0; s < WG_MAXSTAGE; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < WG_MAXSTAGE; ++s) { mbar_init(full0 + 8u * s, 1); mbar_init(empty0 + 8u * s, 1); }
         mbar_init(done_bar, 1);
         fence_barrier_init();
     }
@@ -496,63 +511,72 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     pdl_wait();                                   // prologue above touched no activation; now consume the predecessor's output
-    const int rows = a.n_rows_dev ? min(*a.n_rows_dev, a.M_cap) : a.M_cap;
-    const int ntiles = (rows + WG_TOK - 1) / WG_TOK;
+    int rows = a.n_rows_dev ? min(__ldg(a.n_rows_dev), a.M_cap) : a.M_cap;
+    rows = __reduce_min_sync(0xffffffffu, rows);  // same value in every lane; the reduction lands in a uniform register
+    const int ntiles = (rows + TOK - 1) / TOK;
     const bool have_work = (int)blockIdx.x < ntiles;
 
     if (warp == 0) {
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-                const int s = it % nstage;
-                mbar_wait(empty_bar(s), ((it / nstage) & 1) ^ 1);
-                mbar_expect_tx(full_bar(s), stage_bytes);
-                const uint32_t dst = sbase + s * stage_bytes;
-                for (int nb = 0; nb < NB; ++nb) tma_load_2d(dst + nb * WG_BOX, &tmapY, full_bar(s), nb * 32, tile * WG_TOK);
-                for (int kb = 0; kb < KB; ++kb) tma_load_2d(dst + (NB + kb) * WG_BOX, &tmapX, full_bar(s), kb * 32, tile * WG_TOK);
+        uint32_t s = 0, ph = 1;                   // ph = parity to wait for on the empty barrier of stage s
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            mbar_wait(empty0 + 8u * s, ph);
+            if (elect_one()) {
+                const uint32_t fb = full0 + 8u * s;
+                mbar_expect_tx(fb, stage_bytes);
+                uint32_t dst = sbase + s * stage_bytes;
+                for (int nb = 0; nb < NB; ++nb, dst += BOX) tma_load_2d(dst, &tmapY, fb, nb * 32, tile * TOK);
+                for (int kb = 0; kb < KB; ++kb, dst += BOX) tma_load_2d(dst, &tmapX, fb, kb * 32, tile * TOK);
             }
+            __syncwarp();
+            if (++s == nstage) { s = 0; ph ^= 1; }
         }
     } else if (warp == 1) {
         const uint32_t idesc = idesc_tf32(128, K, 1, 1);
         const uint32_t idesc_b = idesc_tf32(128, 16, 1, 1);
-        const uint64_t ones_desc = smem_desc_sw128_mn32(sbase + WG_OFF_ONES, WG_BOX, 512);
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            const int s = it % nstage;
-            mbar_wait(full_bar(s), (it / nstage) & 1);
-            const uint32_t st_addr = sbase + s * stage_bytes;
-            const int live = rows - tile * WG_TOK;                   // tokens of this tile below the device-side row count
-            if (live < WG_TOK) {
+        const uint64_t ones_desc = smem_desc_sw128_mn32(sbase + WG_OFF_ONES, BOX, 512);
+        // descriptor of stage 0 / token group 0; other stages, token groups and 128-row blocks add a constant to the low word
+        const uint64_t adesc0 = smem_desc_sw128_mn32(sbase, BOX, 512);
+        const uint64_t bdesc0 = smem_desc_sw128_mn32(sbase + NB * BOX, BOX, 512);
+        const uint32_t stage_inc = stage_bytes >> 4, mb_inc = (4u * BOX) >> 4;
+        const bool has_bias = a.boff >= 0;
+        uint32_t s = 0, ph = 0, acc = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            mbar_wait(full0 + 8u * s, ph);
+            const int live = rows - tile * TOK;                      // tokens of this tile below the device-side row count
+            if (live < TOK) {
                 // boundary tile: rows past the live count hold stale workspace data -> zero them (every box, whole 128-B rows)
                 float4* st = reinterpret_cast<float4*>(smem + s * stage_bytes);
                 for (int bx = 0; bx < NB + KB; ++bx)
-                    for (int i = live * 8 + lane; i < WG_TOK * 8; i += 32) st[bx * (WG_BOX / 16) + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int i = live * 8 + lane; i < TOK * 8; i += 32) st[bx * (BOX / 16) + i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 fence_proxy_async();
                 __syncwarp();
             }
             tc_fence_after();
-            if (lane == 0) {
+            const uint64_t a_st = adesc0 + s * stage_inc, b_st = bdesc0 + s * stage_inc;
+            if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < WG_TOK / 8; ++ks) {
-                    const uint64_t bdesc = smem_desc_sw128_mn32(st_addr + NB * WG_BOX + ks * 1024, WG_BOX, 512);
-                    for (int mb = 0; mb < MB; ++mb) {
-                        const uint64_t adesc = smem_desc_sw128_mn32(st_addr + mb * 4 * WG_BOX + ks * 1024, WG_BOX, 512);
-                        umma_tf32(tmem_base + mb * K, adesc, bdesc, idesc, (it | ks) != 0);
-                        if (a.boff >= 0) umma_tf32(tmem_base + bias_col + mb * 16, adesc, ones_desc, idesc_b, (it | ks) != 0);
+                for (int ks = 0; ks < TOK / 8; ++ks) {
+                    const uint64_t bdesc = b_st + ks * 64u;          // 8 tokens = 1024 bytes
+                    uint64_t adesc = a_st + ks * 64u;
+                    for (int mb = 0; mb < MB; ++mb, adesc += mb_inc) {
+                        umma_tf32(tmem_base + mb * K, adesc, bdesc, idesc, acc | ks);
+                        if (has_bias) umma_tf32(tmem_base + bias_col + mb * 16, adesc, ones_desc, idesc_b, acc | ks);
                     }
                 }
-                umma_commit(empty_bar(s));
+                umma_commit(empty0 + 8u * s);
             }
             __syncwarp();
+            acc = 1;
+            if (++s == nstage) { s = 0; ph ^= 1; }
         }
-        if (lane == 0) umma_commit(done_bar);
+        if (elect_one()) umma_commit(done_bar);
         __syncwarp();
     } else {
         // ===== final epilogue: TMEM accumulators -> this CTA's slab of partials =====
         const int quad = warp & 3;
         float* p = a.partial + (size_t)blockIdx.x * a.pstride;
         if (have_work) {
-            mbar_wait(done_bar, 0);
+            mbar_wait_sleep(done_bar, 0);
             tc_fence_after();
         }
         for (int mb = 0; mb < MB; ++mb) {
@@ -634,23 +658,30 @@ int launch_wgrad_tc(const float* dY, const float* X, const int32_t* n_rows_dev, 
                     size_t woff, long long boff, cudaStream_t st) {
     if (N % 32 != 0 || K % 32 != 0 || N > 256 || K > 256 || N + K > 320 || M_cap < 128) return MVN_E_UNSUPPORTED;
     if (!aligned16(dY) || !aligned16(X) || !aligned16(partial) || (pstride % 4) != 0 || (woff % 4) != 0) return MVN_E_UNSUPPORTED;
-    const CUtensorMap* ty = tc::get_tmap_2d(dY, M_cap, N, WG_TOK, true);
-    const CUtensorMap* tx = tc::get_tmap_2d(X, M_cap, K, WG_TOK, true);
+    // 64-token stages halve the per-token barrier / issue overhead; keep 32 where 64 would leave fewer than 3 stages in the ring
+    const int boxes = (N + K) / 32;
+    const int tok = (WG_RING / (boxes * 64 * 128) >= 3) ? 64 : 32;
+    const CUtensorMap* ty = tc::get_tmap_2d(dY, M_cap, N, tok, true);
+    const CUtensorMap* tx = tc::get_tmap_2d(X, M_cap, K, tok, true);
     if (!ty || !tx) return MVN_E_BADARG;
     static bool configured = false;
     if (!configured) {
-        MVN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
+        MVN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
+        MVN_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
         configured = true;
     }
     WgArgs a;
     a.n_rows_dev = n_rows_dev; a.M_cap = M_cap; a.N = N; a.K = K; a.partial = partial; a.pstride = pstride; a.woff = woff; a.boff = boff;
+    a.nstage = WG_RING / (boxes * tok * 128);
+    if (a.nstage > WG_MAXSTAGE) a.nstage = WG_MAXSTAGE;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(kSlabs); cfg.blockDim = dim3(WG_THREADS); cfg.dynamicSmemBytes = WG_SMEM; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    MVN_CUDA(cudaLaunchKernelEx(&cfg, tc_wgrad_kernel, *ty, *tx, a));
+    if (tok == 64) MVN_CUDA(cudaLaunchKernelEx(&cfg, tc_wgrad_kernel<64>, *ty, *tx, a));
+    else MVN_CUDA(cudaLaunchKernelEx(&cfg, tc_wgrad_kernel<32>, *ty, *tx, a));
     MVN_LAUNCH_CHECK();
     return 0;
 }
