@@ -248,6 +248,73 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) ln_bwd_kernel(const float* __r
     }
 }
 
+// Vectorised variant for E in {16, 32, 64, 128}: a lane owns 4 consecutive columns (one 16-byte access), E/4 lanes share
+// a row, so one warp-wide load instruction covers 32/(E/4) rows and U such row groups are in flight per warp before the
+// first reduction -- 1024 threads x U x 32 B of loads outstanding per SM, which is what it takes to keep HBM3e busy from
+// 128 CTAs.  Same slab layout and (fixed) summation order for the dgamma / dbeta partials as the scalar kernel.
+template <int LPR, int U>
+__global__ void __launch_bounds__(LNB_WARPS * 32) ln_bwd_vec_kernel(const float* __restrict__ dY, const float* __restrict__ xhat,
+                                                                    const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                                    float* __restrict__ dZ, const int32_t* n_rows_dev, int M_cap,
+                                                                    float* __restrict__ partial, size_t pstride, size_t goff, size_t boff,
+                                                                    const DropCfg drop) {
+    constexpr int RPW = 32 / LPR, E = LPR * 4;
+    __shared__ float red[LNB_WARPS][32][8];
+    pdl_trigger();
+    const int rows = n_rows_dev ? min(*n_rows_dev, M_cap) : M_cap;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int sub = lane / LPR, cl = lane % LPR;
+    const float4 gam = *reinterpret_cast<const float4*>(gamma + cl * 4);
+    float dg[4] = {0.f, 0.f, 0.f, 0.f}, dbt[4] = {0.f, 0.f, 0.f, 0.f};
+    constexpr float invE = 1.0f / (float)E;
+    const int stride = gridDim.x * LNB_WARPS * RPW;
+    for (int base = (blockIdx.x * LNB_WARPS + wid) * RPW; base < rows; base += U * stride) {
+        float4 dy[U], xh[U];
+        float rs[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int m = base + u * stride + sub;
+            const bool live = m < rows;
+            rs[u] = live ? rstd[m] : 0.f;
+            dy[u] = live ? *reinterpret_cast<const float4*>(dY + (size_t)m * E + cl * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            xh[u] = live ? *reinterpret_cast<const float4*>(xhat + (size_t)m * E + cl * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int m = base + u * stride + sub;
+            if (drop.thresh) {
+                const uint32_t rk = drop_rowkey(drop, (uint32_t)m);
+                dy[u].x *= drop_scale(drop, rk, (uint32_t)(cl * 4)); dy[u].y *= drop_scale(drop, rk, (uint32_t)(cl * 4 + 1));
+                dy[u].z *= drop_scale(drop, rk, (uint32_t)(cl * 4 + 2)); dy[u].w *= drop_scale(drop, rk, (uint32_t)(cl * 4 + 3));
+            }
+            const float g0 = dy[u].x * gam.x, g1 = dy[u].y * gam.y, g2 = dy[u].z * gam.z, g3 = dy[u].w * gam.w;
+            float s1 = (g0 + g1) + (g2 + g3);
+            float s2 = fmaf(g0, xh[u].x, fmaf(g1, xh[u].y, fmaf(g2, xh[u].z, g3 * xh[u].w)));
+            dg[0] = fmaf(dy[u].x, xh[u].x, dg[0]); dg[1] = fmaf(dy[u].y, xh[u].y, dg[1]);
+            dg[2] = fmaf(dy[u].z, xh[u].z, dg[2]); dg[3] = fmaf(dy[u].w, xh[u].w, dg[3]);
+            dbt[0] += dy[u].x; dbt[1] += dy[u].y; dbt[2] += dy[u].z; dbt[3] += dy[u].w;
+            s1 = group_sum<LPR>(s1) * invE; s2 = group_sum<LPR>(s2) * invE;
+            if (m < rows) {
+                const float r = rs[u];
+                *reinterpret_cast<float4*>(dZ + (size_t)m * E + cl * 4) =
+                    make_float4(r * (g0 - s1 - xh[u].x * s2), r * (g1 - s1 - xh[u].y * s2), r * (g2 - s1 - xh[u].z * s2), r * (g3 - s1 - xh[u].w * s2));
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { red[wid][lane][j] = dg[j]; red[wid][lane][4 + j] = dbt[j]; }
+    __syncthreads();
+    float* pp = partial + (size_t)blockIdx.x * pstride;
+    for (int i = threadIdx.x; i < 2 * E; i += blockDim.x) {
+        const int sec = i / E, e = i % E;
+        float s = 0.f;
+        for (int w = 0; w < LNB_WARPS; ++w)
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) s += red[w][r * LPR + (e >> 2)][sec * 4 + (e & 3)];
+        pp[(sec == 0 ? goff : boff) + e] = s;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // pooling: one CTA (128 threads) per sequence, thread e owns column e
 __global__ void __launch_bounds__(128) pool_fwd_kernel(const float* __restrict__ X, const int32_t* __restrict__ cu,
@@ -361,6 +428,16 @@ int launch_ln_bwd(const float* dY, const float* xhat, const float* rstd, const f
     MVN_CHECK_ARG(dY && xhat && rstd && gamma && dZ && partial, "layernorm_bwd: null pointer");
     MVN_UNSUPPORTED(E >= 1 && E <= 128, "layernorm_bwd: E=%d outside [1,128]", E);
     ProfScope prof(PROF_ROW, st);
+    if (aligned16(dY) && aligned16(xhat) && aligned16(dZ) && aligned16(gamma) && (E == 16 || E == 32 || E == 64 || E == 128)) {
+        switch (E) {
+            case 16: ln_bwd_vec_kernel<4, 4><<<kSlabs, LNB_WARPS * 32, 0, st>>>(dY, xhat, rstd, gamma, dZ, n_rows_dev, M_cap, partial, pstride, goff, boff, drop); break;
+            case 32: ln_bwd_vec_kernel<8, 4><<<kSlabs, LNB_WARPS * 32, 0, st>>>(dY, xhat, rstd, gamma, dZ, n_rows_dev, M_cap, partial, pstride, goff, boff, drop); break;
+            case 64: ln_bwd_vec_kernel<16, 4><<<kSlabs, LNB_WARPS * 32, 0, st>>>(dY, xhat, rstd, gamma, dZ, n_rows_dev, M_cap, partial, pstride, goff, boff, drop); break;
+            default: ln_bwd_vec_kernel<32, 4><<<kSlabs, LNB_WARPS * 32, 0, st>>>(dY, xhat, rstd, gamma, dZ, n_rows_dev, M_cap, partial, pstride, goff, boff, drop); break;
+        }
+        MVN_LAUNCH_CHECK();
+        return 0;
+    }
     const int per = (E + 31) / 32;
     switch (per) {
         case 1: ln_bwd_kernel<1><<<kSlabs, LNB_WARPS * 32, 0, st>>>(dY, xhat, rstd, gamma, dZ, n_rows_dev, M_cap, E, partial, pstride, goff, boff, drop); break;

@@ -7,6 +7,7 @@ reference's Python: they are not on the training-step path
 from __future__ import annotations
 
 import math
+import os
 from typing import Any, Dict, List, Optional
 
 import torch
@@ -127,6 +128,9 @@ class MLP(nn.Module):
         return ops.linear(x, lins[-1].weight, lins[-1].bias, 0)
 
 
+_SIDE_STREAMS: Dict[int, List["torch.cuda.Stream"]] = {}       # per device; kept off the module so models stay copyable
+
+
 class LightCurveImageCLIP(_Base):
     """reference: src/models_multimodal.py:98-366."""
 
@@ -172,6 +176,8 @@ class LightCurveImageCLIP(_Base):
         self._gbuf: Optional[torch.Tensor] = None
         self.y_pred, self.y_true = [], []
         self.track_predictions = False      # the reference's epoch-end metric hooks (out of scope) consume these lists
+        # One CUDA stream per modality encoder (see _run_modalities); MVN_CONCURRENT=0 keeps everything on the caller's stream.
+        self.concurrent_modalities = os.environ.get("MVN_CONCURRENT", "1") != "0"
 
     # ---- flat parameter group over the whole model ---------------------------------------------------------
     def flat_group(self) -> ops.FlatParams:
@@ -261,21 +267,45 @@ class LightCurveImageCLIP(_Base):
         z = self.meta_encoder(x_meta)
         return ops.L2NormFn.apply(z) if normalize else z
 
+    def _run_modalities(self, jobs, dev):
+        """The modality encoders are independent until the loss, and each is a chain of short persistent kernels whose
+        launch / prologue / tail gaps leave the SMs idle.  Enqueue every encoder on its own stream so the block scheduler
+        fills one chain's gaps with the other chain's CTAs; autograd replays each encoder's backward on the stream its
+        forward ran on, so the backward chains interleave the same way.  Outputs are joined on the caller's stream."""
+        if not (self.concurrent_modalities and len(jobs) > 1 and dev.type == "cuda"):
+            return [j() for j in jobs]
+        main = torch.cuda.current_stream(dev)
+        side = _SIDE_STREAMS.setdefault(dev.index if dev.index is not None else torch.cuda.current_device(), [])
+        while len(side) < len(jobs) - 1:
+            side.append(torch.cuda.Stream(device=dev))
+        streams = [main] + side[:len(jobs) - 1]
+        for s in streams[1:]:
+            s.wait_stream(main)
+        outs = []
+        for j, s in zip(jobs, streams):
+            with torch.cuda.stream(s):
+                outs.append(j())
+        for o, s in zip(outs[1:], streams[1:]):
+            main.wait_stream(s)
+            o.record_stream(main)
+        return outs
+
     def forward(self, x_img, x_lc, t_lc, mask_lc, x_sp, t_sp, mask_sp, redshift=None, classification=None):
         head = self.regression or self.classification
         g = self.flat_group()
         dev = next(self.parameters()).device
         g.ensure()
         self._new_gbuf(g, dev)
-        x = []
+        jobs = []                      # list order is fixed [host_galaxy, lightcurve, spectral, meta] (reference :260-273)
         if "host_galaxy" in self.combinations:
-            x.append(self._img_embed(x_img, g, not head))
+            jobs.append(lambda: self._img_embed(x_img, g, not head))
         if "lightcurve" in self.combinations:
-            x.append(self._seq_embed("lightcurve", x_lc, t_lc, mask_lc, g, not head))
+            jobs.append(lambda: self._seq_embed("lightcurve", x_lc, t_lc, mask_lc, g, not head))
         if "spectral" in self.combinations:
-            x.append(self._seq_embed("spectral", x_sp, t_sp, mask_sp, g, not head))
+            jobs.append(lambda: self._seq_embed("spectral", x_sp, t_sp, mask_sp, g, not head))
         if "meta" in self.combinations:
-            x.append(self._meta_embed(classification, redshift, not head))
+            jobs.append(lambda: self._meta_embed(classification, redshift, not head))
+        x = self._run_modalities(jobs, dev)
         if head:
             return ops.linear(torch.cat(x, dim=-1) if len(x) > 1 else x[0], self.linear.weight, self.linear.bias, 0)
         return x
