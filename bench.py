@@ -29,19 +29,31 @@ WORKLOADS = {
                lc=dict(n_out=32, emb=64, heads=8, depth=5, time_norm=20583.369161312577, agg="mean"),
                sp=dict(n_out=32, emb=32, heads=2, depth=13, time_norm=17945.142213594805, agg="mean"),
                T_lc=200, T_sp=220),
+    "c3": dict(desc="C3 maven-lite bimodal on ZTFBTS-shaped batches: lightcurve(E64,h8,L5,T200,2 bands)+host_galaxy ConvMixer(dim32,depth2,k5,p10, 3x60x60) CLIP",
+               combinations=["lightcurve", "host_galaxy"], img=True, lc_dist="ztfbts",
+               lc=dict(n_out=32, emb=64, heads=8, depth=5, time_norm=20583.369161312577, agg="mean"), sp=None, T_lc=200, T_sp=0),
+    "c5": dict(desc="C5 trimodal: lightcurve(E64,h8,L5,T200)+spectral(E32,h2,L13,T220)+host_galaxy ConvMixer(dim32,depth2,k5,p10, 3x60x60) CLIP, 3 pairs",
+               combinations=["lightcurve", "spectral", "host_galaxy"], img=True,
+               lc=dict(n_out=32, emb=64, heads=8, depth=5, time_norm=20583.369161312577, agg="mean"),
+               sp=dict(n_out=32, emb=32, heads=2, depth=13, time_norm=17945.142213594805, agg="mean"),
+               T_lc=200, T_sp=220),
     "c2": dict(desc="C2 lc_5way_f1 shape: lightcurve(E32,h2,L9,T200) 5-way classifier",
                combinations=["lightcurve"], classification=True, n_classes=5,
                lc=dict(n_out=32, emb=32, heads=2, depth=9, time_norm=3371.17, agg="mean"), sp=None, T_lc=200, T_sp=0),
 }
+CONV = dict(dim=32, depth=2, channels=3, kernel_size=5, patch_size=10, n_out=32)      # configs/maven-lite.yaml:12-22
 LR, WD, LOGIT_SCALE = 3.716367614864064e-05, 0.000555522900788888, 19.545966923442453
 
 
 # --------------------------------------------------------------------------------------------------
 # synthetic data, generated on the CPU with a fixed seed
 # --------------------------------------------------------------------------------------------------
-def make_seq(gen, B, T, nband, lo, hi, tmax, t0):
+def make_seq(gen, B, T, nband, lo, hi, tmax, t0, lognormal=False):
     per = T // nband
-    n = torch.randint(lo, min(hi, per) + 1, (B, nband), generator=gen)
+    if lognormal:     # ZTFBTS shape: n_obs per band ~ clip(round(LogNormal(ln 8, 0.7)), 1, 100)
+        n = torch.exp(math.log(8.0) + 0.7 * torch.randn(B, nband, generator=gen)).round().clamp(1, min(hi, per)).long()
+    else:
+        n = torch.randint(lo, min(hi, per) + 1, (B, nband), generator=gen)
     pos = torch.arange(per)[None, None, :]
     valid = pos < n[:, :, None]                                             # (B, nband, per)
     t = torch.rand(B, nband, per, generator=gen) * tmax
@@ -54,14 +66,16 @@ def make_seq(gen, B, T, nband, lo, hi, tmax, t0):
 
 def make_batch(wl, B, seed):
     gen = torch.Generator().manual_seed(seed)
-    x_lc, t_lc, m_lc = make_seq(gen, B, wl["T_lc"], 2, 20, 100, 300.0, 0.0)           # sim-pretrain shape: Uniform{20..100}/band
+    x_lc, t_lc, m_lc = make_seq(gen, B, wl["T_lc"], 2, 20, 100, 300.0, 0.0,           # sim-pretrain shape: Uniform{20..100}/band
+                                lognormal=wl.get("lc_dist") == "ztfbts")
     if wl["sp"] is not None:
         x_sp, t_sp, m_sp = make_seq(gen, B, wl["T_sp"], 1, 110, 220, 5500.0, 3700.0)   # valid length Uniform{110..220}
     else:
         x_sp = t_sp = m_sp = None
     cls = torch.randint(0, 5, (B,), generator=gen)
     red = torch.rand(B, generator=gen)
-    return [None, x_lc, t_lc, m_lc, x_sp, t_sp, m_sp, red, cls]
+    x_img = torch.rand(B, 3, 60, 60, generator=gen) if wl.get("img") else None          # host-galaxy cut-outs, Uniform(0,1) fp32
+    return [x_img, x_lc, t_lc, m_lc, x_sp, t_sp, m_sp, red, cls]
 
 
 def model_kwargs(wl, dropout):
@@ -69,6 +83,8 @@ def model_kwargs(wl, dropout):
               combinations=wl["combinations"], transformer_kwargs={**wl["lc"], "dropout": dropout})
     if wl["sp"] is not None:
         kw["transformer_spectral_kwargs"] = {**wl["sp"], "dropout": dropout}
+    if wl.get("img"):
+        kw["conv_kwargs"] = {**CONV, "dropout_prob": dropout}       # script_wandb.py:151: the CNN shares cfg.dropout
     if wl.get("classification"):
         kw.update(classification=True, n_classes=wl["n_classes"])
     return kw
@@ -78,7 +94,13 @@ def flops_per_step(wl, batch):
     """Algorithmic FLOPs of one training step, two accountings: dense over the padded T (comparable with
     the reference) and executed (valid tokens only).  Returned per kernel class for the executed accounting."""
     out = {"padded_train": 0.0, "gemm": 0.0, "wgrad": 0.0, "attn_fwd": 0.0, "attn_bwd": 0.0,
-           "bytes": {"gemm": 0.0, "wgrad": 0.0, "attn_fwd": 0.0, "attn_bwd": 0.0, "row": 0.0}}
+           "bytes": {"gemm": 0.0, "wgrad": 0.0, "attn_fwd": 0.0, "attn_bwd": 0.0, "row": 0.0, "conv": 0.0}}
+    if wl.get("img"):
+        # ConvMixer (SURVEY §8d): ~1.1 MFLOP fwd per sample, train ~3x; bytes = the fp32 image once forward and once more for the
+        # patch-conv weight gradient, plus the 128-B embedding
+        Bn = batch[0].shape[0]
+        out["padded_train"] += 3.3e6 * Bn
+        out["bytes"]["conv"] += Bn * (2 * 43200.0 + 128.0)
     for key, m_idx, T in (("lc", 3, wl["T_lc"]), ("sp", 6, wl["T_sp"])):
         kw = wl[key]
         if kw is None:
@@ -204,7 +226,7 @@ def cpu_reference_steps(wl, sample_B, steps, warmup, threads):
     params = [v for v in sd.values() if v.requires_grad]
     opt = torch.optim.RAdam(params, lr=LR, weight_decay=WD)
     cfg = dict(combinations=wl["combinations"], nband=2, transformer_kwargs=wl["lc"], transformer_spectral_kwargs=wl["sp"],
-               classification=wl.get("classification", False), n_classes=wl.get("n_classes", 5))
+               classification=wl.get("classification", False), n_classes=wl.get("n_classes", 5), conv_kwargs=CONV)
     batch = make_batch(wl, sample_B, seed=1234)
     times = []
     for i in range(warmup + steps):
@@ -264,7 +286,7 @@ def run_gpu(args):
     host = make_batch(wl, B, seed=1000 + rank)                 # each rank owns its shard of the global batch
     pinned = [None if v is None else v.pin_memory() for v in host]
     resident = [None if v is None else v.to(dev) for v in host]
-    h2d = sum(v.numel() * v.element_size() for v in (pinned[1:7]) if v is not None)
+    h2d = sum(v.numel() * v.element_size() for v in (pinned[0:7]) if v is not None)
     if wl.get("classification"):
         h2d += pinned[8].numel() * pinned[8].element_size()
     fl = flops_per_step(wl, host)
@@ -374,7 +396,7 @@ def run_gpu(args):
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(args.precision, {}).get(top)
     classes = {}
-    for k in ("gemm", "wgrad", "attn_fwd", "attn_bwd", "row"):
+    for k in ("gemm", "wgrad", "attn_fwd", "attn_bwd", "row", "conv"):
         ms_k = breakdown[k]["ms"]
         if ms_k > 0:
             classes[k] = {"ms": ms_k, "algorithmic_GBps": fl["bytes"][k] / (ms_k / 1e3) / 1e9, "frac_hbm": fl["bytes"][k] / (ms_k / 1e3) / 1e9 / hbm}

@@ -174,6 +174,10 @@ int mvn_seq_encoder_bwd(const mvn_seq_cfg* cfg, const float* params, const float
  * packed [rows, cols] activation: site 0 = transformer input, 1+2l / 2+2l = after norm1 / norm2 of layer l
  * (src/transformer_utils.py:147,112,115).  Lets a caller reproduce or test a dropped-out forward exactly. */
 int mvn_dropout_scale(uint64_t seed, int site, float p, int rows, int cols, float* out, void* stream);
+/* nn.Dropout as a standalone op (MLP heads src/models_multimodal.py:834-857; TransformerBlock / Transformer used on their own,
+ * src/transformer_utils.py:112,115,147): y[r,c] = x[r,c] * keep-factor(seed, site, r, c).  The backward is the same call on the
+ * gradient (the mask is regenerated, never stored).  x == y (in place) is allowed. */
+int mvn_dropout_apply(const float* x, float* y, int rows, int cols, uint64_t seed, int site, float p, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * A10/A11: symmetric InfoNCE, streamed; the N x N logits are never written.  src/loss.py:14-38.
@@ -213,6 +217,10 @@ typedef struct {
     int32_t normalize, training, prec;
     float   bn_eps, bn_momentum;
     int64_t global_count;   /* B*Hp*Wp summed over ranks (== local count on one GPU) */
+    float   dropout_p;      /* nn.Dropout p of ConvMixer (src/models_multimodal.py:62-77,85-87); applied when training!=0.
+                               Site s in 1..2*depth follows BatchNorm s, site 1+2*depth follows the head's GELU; the mask of
+                               element [row, col] at a site is mvn_dropout_scale(seed, site, p, ...) and is regenerated in the backward */
+    uint64_t seed;          /* dropout seed of THIS call (ignored when dropout_p==0) */
 } mvn_conv_cfg;
 
 size_t mvn_conv_param_count(const mvn_conv_cfg* cfg);

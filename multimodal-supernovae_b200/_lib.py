@@ -22,7 +22,7 @@ class ConvCfg(Structure):
     _fields_ = [("B", c_int32), ("C", c_int32), ("H", c_int32), ("W", c_int32), ("dim", c_int32), ("depth", c_int32),
                 ("kernel_size", c_int32), ("patch_size", c_int32), ("n_out", c_int32), ("enc_dim", c_int32), ("hidden", c_int32),
                 ("normalize", c_int32), ("training", c_int32), ("prec", c_int32), ("bn_eps", c_float), ("bn_momentum", c_float),
-                ("global_count", c_int64)]
+                ("global_count", c_int64), ("dropout_p", c_float), ("seed", c_uint64)]
 
 
 P = c_void_p
@@ -54,6 +54,7 @@ _SIGS = {
     "mvn_l2norm_fwd": (c_int, [P, P, P, c_int, c_int, P]),
     "mvn_l2norm_bwd": (c_int, [P, P, P, P, c_int, c_int, P]),
     "mvn_dropout_scale": (c_int, [c_uint64, c_int, c_float, c_int, c_int, P, P]),
+    "mvn_dropout_apply": (c_int, [P, P, c_int, c_int, c_uint64, c_int, c_float, P]),
     "mvn_seq_param_count": (c_size_t, [POINTER(SeqCfg)]),
     "mvn_seq_workspace_bytes": (c_size_t, [POINTER(SeqCfg)]),
     "mvn_seq_encoder_fwd": (c_int, [POINTER(SeqCfg), P, P, P, P, P, P, P, c_size_t, P]),

@@ -39,16 +39,18 @@ static cudaEvent_t take_event() {
     if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
     cudaEvent_t e; cudaEventCreate(&e); return e;
 }
+static thread_local int g_prof_depth = 0;      // a scope opened inside another one (ConvMixer stage -> its GEMMs) belongs to the outer class
 ProfScope::ProfScope(int cls_, cudaStream_t st_) : cls(cls_), st(st_), stop(nullptr), on(false) {
-    if (g_prof_mask & (1u << cls)) {
+    if ((g_prof_mask & (1u << cls)) && g_prof_depth == 0) {
         on = true;
+        ++g_prof_depth;
         cudaEvent_t a = take_event();
         stop = take_event();
         cudaEventRecord(a, st);
         g_prof[cls].push_back({a, stop});
     }
 }
-ProfScope::~ProfScope() { if (on) cudaEventRecord(stop, st); }
+ProfScope::~ProfScope() { if (on) { cudaEventRecord(stop, st); --g_prof_depth; } }
 }  // namespace mvn
 
 extern "C" void mvn_prof_enable(unsigned class_mask) { mvn::g_prof_mask = class_mask; }

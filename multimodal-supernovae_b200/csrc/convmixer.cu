@@ -101,6 +101,13 @@ ConvWs conv_carve(const mvn_conv_cfg& c, void* base) {
     return w;
 }
 
+// Dropout sites: s = 1..2*depth follows BatchNorm s of the mixer layers (the patch BN, s = 0, has none); s = 1+2*depth is
+// the projection head's dropout after its GELU.  Element index = (row of the [R,dim] / [B,hidden] matrix, column).
+DropCfg conv_drop(const mvn_conv_cfg& c, int site) {
+    if (!c.training || site == 0) return DropCfg();
+    return make_drop(c.dropout_p, c.seed, (uint32_t)site);
+}
+
 int conv_check(const mvn_conv_cfg* c) {
     MVN_CHECK_ARG(c != nullptr, "convmixer: null cfg");
     MVN_CHECK_ARG(c->B > 0 && c->C > 0 && c->H > 0 && c->W > 0 && c->dim > 0 && c->depth >= 0 && c->n_out > 0 && c->hidden > 0 && c->enc_dim >= 0,
@@ -110,6 +117,7 @@ int conv_check(const mvn_conv_cfg* c) {
     MVN_UNSUPPORTED(c->kernel_size % 2 == 1 && c->kernel_size <= 9, "convmixer: kernel_size=%d must be odd and <= 9", c->kernel_size);
     MVN_UNSUPPORTED((c->C * c->patch_size * c->patch_size) % 4 == 0, "convmixer: C*p*p must be a multiple of 4");
     MVN_CHECK_ARG((long long)c->B * (c->H / c->patch_size) * (c->W / c->patch_size) < (1ll << 30), "convmixer: too many patches");
+    MVN_CHECK_ARG(c->dropout_p >= 0.0f && c->dropout_p < 1.0f, "convmixer: dropout_p=%g outside [0,1)", (double)c->dropout_p);
     return 0;
 }
 
@@ -188,12 +196,13 @@ __global__ void bn_coeffs_kernel(const double* __restrict__ stats, double count,
     const float sc = gamma[c] * rs;
     scale_o[c] = sc; shift_o[c] = beta[c] - mean * sc;
 }
-// z = a*scale + shift (+ res)
+// z = dropout(a*scale + shift) (+ res)      (nn.Dropout follows every mixer BatchNorm, src/models_multimodal.py:62-77)
 __global__ void bn_apply_kernel(const float* __restrict__ a, const float* __restrict__ scale, const float* __restrict__ shift,
-                                const float* __restrict__ res, float* __restrict__ z, size_t n, int dim) {
+                                const float* __restrict__ res, float* __restrict__ z, size_t n, int dim, const DropCfg drop) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % dim);
         float v = fmaf(a[i], scale[c], shift[c]);
+        if (drop.thresh) v *= drop_scale(drop, drop_rowkey(drop, (uint32_t)(i / dim)), (uint32_t)c);
         if (res) v += res[i];
         z[i] = v;
     }
@@ -268,18 +277,21 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ dpooled, int B, int
 }
 // BN backward statistics: per channel sum(dout), sum(dout*xhat), xhat = (a-mean)*rstd
 __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const float* __restrict__ dout, const float* __restrict__ a, const float* __restrict__ mean,
-                                                           const float* __restrict__ rstd, int R, int dim, double* __restrict__ stat_part) {
+                                                           const float* __restrict__ rstd, int R, int dim, double* __restrict__ stat_part,
+                                                           const DropCfg drop) {
     __shared__ double red[8][2][128];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f}, mu[4], rs[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) { const int c = lane + 32 * q; mu[q] = c < dim ? mean[c] : 0.f; rs[q] = c < dim ? rstd[c] : 0.f; }
     for (int r = blockIdx.x * 8 + wid; r < R; r += gridDim.x * 8) {
+        const uint32_t rk = drop.thresh ? drop_rowkey(drop, (uint32_t)r) : 0u;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int c = lane + 32 * q;
             if (c < dim) {
-                const float g = dout[(size_t)r * dim + c];
+                float g = dout[(size_t)r * dim + c];
+                if (drop.thresh) g *= drop_scale(drop, rk, (uint32_t)c);     // dout is the gradient AFTER this BN's dropout
                 const float xh = (a[(size_t)r * dim + c] - mu[q]) * rs[q];
                 s1[q] += g; s2[q] = fmaf(g, xh, s2[q]);
             }
@@ -308,12 +320,15 @@ __global__ void bn_bwd_reduce_kernel(const double* __restrict__ part, int nblk, 
 // du = gelu'(u) * scale * (dout - S1/N - xhat*S2/N)
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ a, const float* __restrict__ u,
                                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
-                                    const double* __restrict__ stats, double count, size_t n, int dim, float* __restrict__ du) {
+                                    const double* __restrict__ stats, double count, size_t n, int dim, float* __restrict__ du,
+                                    const DropCfg drop) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % dim);
         const float xh = (a[i] - mean[c]) * rstd[c];
         const float m1 = (float)(stats[c] / count), m2 = (float)(stats[dim + c] / count);
-        const float da = scale[c] * (dout[i] - m1 - xh * m2);
+        float g = dout[i];
+        if (drop.thresh) g *= drop_scale(drop, drop_rowkey(drop, (uint32_t)(i / dim)), (uint32_t)c);
+        const float da = scale[c] * (g - m1 - xh * m2);
         du[i] = da * gelu_erf_grad(u[i]);
     }
 }
@@ -323,8 +338,13 @@ __global__ void bn_bwd_eval_kernel(const float* __restrict__ dout, const float* 
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         du[i] = dout[i] * scale[(int)(i % dim)] * gelu_erf_grad(u[i]);
 }
-__global__ void gelu_pair_kernel(const float* __restrict__ u, float* __restrict__ h, size_t n) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) h[i] = gelu_erf(u[i]);
+// h = dropout(gelu(u)), rows of `cols` elements   (projection head, src/models_multimodal.py:85-87)
+__global__ void gelu_pair_kernel(const float* __restrict__ u, float* __restrict__ h, size_t n, int cols, const DropCfg drop) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float v = gelu_erf(u[i]);
+        if (drop.thresh) v *= drop_scale(drop, drop_rowkey(drop, (uint32_t)(i / cols)), (uint32_t)(i % cols));
+        h[i] = v;
+    }
 }
 
 inline int ew_blocks(size_t n) { size_t b = (n + 255) / 256; return (int)(b < 4096 ? (b ? b : 1) : 4096); }
@@ -363,7 +383,7 @@ extern "C" int mvn_convmixer_fwd_stage(const mvn_conv_cfg* cfg, int stage, const
                                                          c.training, running_stats + (size_t)s * 2 * dim, dim, bn.mean, bn.rstd, bn.scale, bn.shift);
         MVN_LAUNCH_CHECK();
         const float* res = (s & 1) ? w.bn(s - 1).z : nullptr;      // "A" BNs sit inside the Residual: add the layer input
-        bn_apply_kernel<<<ew_blocks(n), 256, 0, st>>>(bn.a, bn.scale, bn.shift, res, bn.z, n, dim);
+        bn_apply_kernel<<<ew_blocks(n), 256, 0, st>>>(bn.a, bn.scale, bn.shift, res, bn.z, n, dim, conv_drop(c, s));
         MVN_LAUNCH_CHECK();
         return 0;
     };
@@ -408,7 +428,7 @@ extern "C" int mvn_convmixer_fwd_stage(const mvn_conv_cfg* cfg, int stage, const
     GemmEpilogue e1;
     e1.bias = params + o.fc1_b;
     MVN_TRY(launch_gemm(w.pooled, params + o.fc1_w, w.u1, nullptr, c.B, c.hidden, dim, true, e1, 0, st));
-    gelu_pair_kernel<<<ew_blocks((size_t)c.B * c.hidden), 256, 0, st>>>(w.u1, w.h1, (size_t)c.B * c.hidden);
+    gelu_pair_kernel<<<ew_blocks((size_t)c.B * c.hidden), 256, 0, st>>>(w.u1, w.h1, (size_t)c.B * c.hidden, c.hidden, conv_drop(c, nbn));
     MVN_LAUNCH_CHECK();
     GemmEpilogue e2;
     e2.bias = params + o.fc2_b;
@@ -456,7 +476,7 @@ extern "C" int mvn_convmixer_bwd_stage(const mvn_conv_cfg* cfg, int stage, const
         size_t g, b;
         bn_param(o, s, &g, &b);
         const ConvWs::Bn bn = w.bn(s);
-        bn_bwd_stats_kernel<<<kSlabs, 256, 0, st>>>(w.dZ, bn.a, bn.mean, bn.rstd, R, dim, w.stat_part);
+        bn_bwd_stats_kernel<<<kSlabs, 256, 0, st>>>(w.dZ, bn.a, bn.mean, bn.rstd, R, dim, w.stat_part, conv_drop(c, s));
         MVN_LAUNCH_CHECK();
         bn_bwd_reduce_kernel<<<cdiv(2 * dim, 128), 128, 0, st>>>(w.stat_part, kSlabs, dim, bn_stats_bwd + (size_t)s * 2 * dim, grads + g, grads + b);
         MVN_LAUNCH_CHECK();
@@ -481,6 +501,7 @@ extern "C" int mvn_convmixer_bwd_stage(const mvn_conv_cfg* cfg, int stage, const
         MVN_TRY(launch_wgrad_partials(df, w.h1, nullptr, c.B, c.n_out, c.hidden, part, ps, o.fc2_w, (long long)o.fc2_b, 0, st));
         GemmEpilogue eg;
         eg.act_src = w.u1; eg.dact = 2;
+        eg.drop = conv_drop(c, nbn);
         MVN_TRY(launch_gemm(df, params + o.fc2_w, w.du1, nullptr, c.B, c.hidden, c.n_out, false, eg, 0, st));
         MVN_TRY(launch_wgrad_partials(w.du1, w.pooled, nullptr, c.B, c.hidden, dim, part, ps, o.fc1_w, (long long)o.fc1_b, 0, st));
         MVN_TRY(launch_gemm(w.du1, params + o.fc1_w, w.dpooled, nullptr, c.B, dim, c.hidden, false, e0, 0, st));
@@ -494,7 +515,8 @@ extern "C" int mvn_convmixer_bwd_stage(const mvn_conv_cfg* cfg, int stage, const
     const int s = stage;
     const ConvWs::Bn bn = w.bn(s);
     if (c.training) {
-        bn_bwd_apply_kernel<<<ew_blocks(n), 256, 0, st>>>(w.dZ, bn.a, bn.u, bn.mean, bn.rstd, bn.scale, bn_stats_bwd + (size_t)s * 2 * dim, count, n, dim, w.dU);
+        bn_bwd_apply_kernel<<<ew_blocks(n), 256, 0, st>>>(w.dZ, bn.a, bn.u, bn.mean, bn.rstd, bn.scale, bn_stats_bwd + (size_t)s * 2 * dim, count, n, dim, w.dU,
+                                                           conv_drop(c, s));
     } else {
         bn_bwd_eval_kernel<<<ew_blocks(n), 256, 0, st>>>(w.dZ, bn.u, bn.scale, n, dim, w.dU);
     }

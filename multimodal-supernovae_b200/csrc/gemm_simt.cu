@@ -154,6 +154,11 @@ __global__ void __launch_bounds__((BM / 4) * (BN / 4)) gemm_kernel(const GemmArg
                     else if (ep.dact == 2) v[j] *= gelu_erf_grad(ep.act_src[(size_t)m * N + n]);
                 }
             }
+            if (ep.drop.thresh) {       // dropout after the activation (forward) / mask of the forward's dropout (dact: backward)
+                const uint32_t rk = drop_rowkey(ep.drop, (uint32_t)m);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] *= drop_scale(ep.drop, rk, (uint32_t)(nb + j));
+            }
             float* c = a.C + (size_t)m * N + nb;
             if (a.vecC && nb + 3 < N) {
                 *reinterpret_cast<float4*>(c) = make_float4(v[0], v[1], v[2], v[3]);
@@ -268,7 +273,7 @@ int launch_gemm(const float* A, const float* Bm, float* C, const int32_t* n_rows
                 bool b_is_nk, const GemmEpilogue& ep, int prec, cudaStream_t st) {
     MVN_CHECK_ARG(A && Bm && C && M_cap > 0 && N > 0 && K > 0, "gemm: null pointer or non-positive size (M=%d N=%d K=%d)", M_cap, N, K);
     ProfScope prof(PROF_GEMM, st);
-    if (prec == 1) {
+    if (prec == 1 && !(ep.drop.thresh && !ep.gamma)) {     // the tensor-core epilogue applies dropout only after LayerNorm
         int r = launch_gemm_tc(A, Bm, C, n_rows_dev, M_cap, N, K, b_is_nk, ep, st);
         if (r != MVN_E_UNSUPPORTED) return r;     // shapes the tensor-core kernel does not cover use the FFMA kernel
     }

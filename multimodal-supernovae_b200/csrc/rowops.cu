@@ -482,9 +482,42 @@ __global__ void dropout_scale_kernel(const DropCfg drop, size_t n, int cols, flo
         out[i] = drop.thresh ? drop_scale(drop, drop_rowkey(drop, (uint32_t)(i / cols)), (uint32_t)(i % cols)) : 1.0f;
 }
 
+// y = x * keep-factor (vectorised when cols % 4 == 0); the same call with dy -> dx is the backward
+__global__ void dropout_apply_kernel(const DropCfg drop, const float* __restrict__ x, float* __restrict__ y, size_t n, int cols, int vec) {
+    if (vec) {
+        const size_t n4 = n / 4;
+        const int c4 = cols / 4;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+            float4 v = reinterpret_cast<const float4*>(x)[i];
+            const uint32_t rk = drop_rowkey(drop, (uint32_t)(i / c4)), c = (uint32_t)(i % c4) * 4u;
+            v.x *= drop_scale(drop, rk, c); v.y *= drop_scale(drop, rk, c + 1); v.z *= drop_scale(drop, rk, c + 2); v.w *= drop_scale(drop, rk, c + 3);
+            reinterpret_cast<float4*>(y)[i] = v;
+        }
+        return;
+    }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        y[i] = x[i] * drop_scale(drop, drop_rowkey(drop, (uint32_t)(i / cols)), (uint32_t)(i % cols));
+}
+
 }  // namespace mvn
 
 using namespace mvn;
+
+extern "C" int mvn_dropout_apply(const float* x, float* y, int rows, int cols, uint64_t seed, int site, float p, void* stream) {
+    MVN_CHECK_ARG(x && y && rows > 0 && cols > 0 && p >= 0.f && p < 1.f && site >= 0, "dropout_apply: bad arguments");
+    const size_t n = (size_t)rows * cols;
+    if (!(p > 0.f)) {
+        if (x != y) MVN_CUDA(cudaMemcpyAsync(y, x, n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        return 0;
+    }
+    const int vec = (cols % 4 == 0) && aligned16(x) && aligned16(y);
+    const size_t work = vec ? n / 4 : n;
+    const int blocks = (int)((work + 255) / 256 < (size_t)(8 * num_sms()) ? (work + 255) / 256 : (size_t)(8 * num_sms()));
+    ProfScope prof(PROF_ROW, (cudaStream_t)stream);
+    dropout_apply_kernel<<<blocks > 0 ? blocks : 1, 256, 0, (cudaStream_t)stream>>>(make_drop(p, seed, (uint32_t)site), x, y, n, cols, vec);
+    MVN_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int mvn_dropout_scale(uint64_t seed, int site, float p, int rows, int cols, float* out, void* stream) {
     MVN_CHECK_ARG(out && rows > 0 && cols > 0 && p >= 0.f && p < 1.f && site >= 0, "dropout_scale: bad arguments");

@@ -90,12 +90,12 @@ class ConvMixer(nn.Module):
         return ps
 
     def run_fused(self, x, *, group: ops.FlatParams, pidx, extra_params, enc_dim: int, normalize: bool, gbuf=None, goff=0):
-        if self.training and self.dropout_prob > 0:
-            raise NotImplementedError("maven_b200: ConvMixer dropout>0 in train mode is not built yet (parity runs use dropout=0)")
+        p_drop = float(self.dropout_prob) if self.training else 0.0
+        seed = ops.next_dropout_seed(self) if p_drop > 0.0 else 0
         flat = group.ensure()
         off = group.offsets[pidx[0]]
         count = group.offsets[pidx[1]] - off
-        call = ops.ConvCall(self, flat, off, count, group, pidx, enc_dim, normalize, _prec_of(self), gbuf, goff)
+        call = ops.ConvCall(self, flat, off, count, group, pidx, enc_dim, normalize, _prec_of(self), gbuf, goff, p_drop, seed)
         return ops.ConvMixerFn.apply(x, call, *extra_params)
 
     def forward(self, x):
@@ -120,11 +120,11 @@ class MLP(nn.Module):
         self.layers.append(nn.Linear(hidden_dim, output_dim))
 
     def forward(self, x):
-        if self.training and self.dropout > 0:
-            raise NotImplementedError("maven_b200: MLP dropout>0 in train mode is not built yet")
+        p = float(self.dropout) if self.training else 0.0
+        seed = ops.next_dropout_seed(self) if p > 0.0 else 0
         lins = [m for m in self.layers if isinstance(m, nn.Linear)]
-        for lin in lins[:-1]:
-            x = ops.LinearReluFn.apply(x, lin.weight, lin.bias, 0)
+        for site, lin in enumerate(lins[:-1]):                  # Linear -> ReLU -> Dropout (site = hidden layer index)
+            x = ops.dropout(ops.LinearReluFn.apply(x, lin.weight, lin.bias, 0), p, seed, site)
         return ops.linear(x, lins[-1].weight, lins[-1].bias, 0)
 
 

@@ -262,6 +262,50 @@ class LinearReluFn(torch.autograd.Function):
         return dx.view(ctx.shp), dw, db, None
 
 
+def next_dropout_seed(module) -> int:
+    """A fresh 64-bit dropout seed per training-mode call (the kernels regenerate their counter-based masks from it in
+    the backward): torch's seed, a per-module call counter and the data-parallel rank (shards draw different masks), so
+    runs are reproducible under torch.manual_seed; `module.dropout_seed` pins it."""
+    fixed = getattr(module, "dropout_seed", None)
+    if fixed is not None:
+        return int(fixed) & 0xFFFFFFFFFFFFFFFF
+    module._drop_calls = getattr(module, "_drop_calls", 0) + 1
+    rank = 0
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        rank = torch.distributed.get_rank()
+    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + module._drop_calls * 0xD1B54A32D192ED03 + (id(module) % 65521) * 0x2545F491
+            + rank * 0x9FB21C651E98DF25) & 0xFFFFFFFFFFFFFFFF
+
+
+class DropoutFn(torch.autograd.Function):
+    """nn.Dropout over the last dimension's rows with the library's counter-based mask (mvn_dropout_apply); the backward
+    regenerates the mask from (seed, site)."""
+
+    @staticmethod
+    def forward(ctx, x, p: float, seed: int, site: int):
+        L = lib()
+        x2 = _req(x, "x").reshape(-1, x.shape[-1])
+        y = torch.empty_like(x2)
+        check(L.mvn_dropout_apply(_p(x2), _p(y), x2.shape[0], x2.shape[1], seed, site, p, _stream()), "dropout_apply")
+        _count(1)
+        ctx.meta = (p, seed, site)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = lib()
+        p, seed, site = ctx.meta
+        d2 = _req(dy, "grad_output").reshape(-1, dy.shape[-1])
+        dx = torch.empty_like(d2)
+        check(L.mvn_dropout_apply(_p(d2), _p(dx), d2.shape[0], d2.shape[1], seed, site, p, _stream()), "dropout_apply")
+        _count(1)
+        return dx.view(dy.shape), None, None, None
+
+
+def dropout(x, p: float, seed: int, site: int = 0):
+    return x if not (p > 0.0) else DropoutFn.apply(x, float(p), int(seed), int(site))
+
+
 class L2NormFn(torch.autograd.Function):
     """x / ||x||_2 over the last dimension, no epsilon (src/models_multimodal.py:279,286,293)."""
 
@@ -415,11 +459,12 @@ class AttentionFn(torch.autograd.Function):
 
 
 class ConvCall:
-    __slots__ = ("module", "flat", "off", "count", "group", "pidx", "enc_dim", "normalize", "prec", "gbuf", "goff")
+    __slots__ = ("module", "flat", "off", "count", "group", "pidx", "enc_dim", "normalize", "prec", "gbuf", "goff", "dropout_p", "seed")
 
-    def __init__(self, module, flat, off, count, group, pidx, enc_dim, normalize, prec, gbuf=None, goff=0):
+    def __init__(self, module, flat, off, count, group, pidx, enc_dim, normalize, prec, gbuf=None, goff=0, dropout_p=0.0, seed=0):
         self.module, self.flat, self.off, self.count, self.group, self.pidx = module, flat, off, count, group, pidx
         self.enc_dim, self.normalize, self.prec, self.gbuf, self.goff = enc_dim, normalize, prec, gbuf, goff
+        self.dropout_p, self.seed = dropout_p, seed
 
 
 class ConvMixerFn(torch.autograd.Function):
@@ -447,7 +492,7 @@ class ConvMixerFn(torch.autograd.Function):
         cfg = ConvCfg(B=B, C=C, H=H, W=W, dim=m.dim, depth=m.depth, kernel_size=m.kernel_size, patch_size=m.patch_size, n_out=m.n_out,
                       enc_dim=call.enc_dim, hidden=m.projection[2].out_features, normalize=1 if call.normalize else 0,
                       training=1 if m.training else 0, prec=call.prec, bn_eps=bn0.eps, bn_momentum=bn0.momentum if bn0.momentum is not None else 0.1,
-                      global_count=B * P * world)
+                      global_count=B * P * world, dropout_p=call.dropout_p if m.training else 0.0, seed=call.seed)
         need = L.mvn_conv_param_count(ctypes.byref(cfg))
         if need != call.count:
             raise RuntimeError(f"maven_b200: ConvMixer parameter layout mismatch (library {need}, module {call.count}): "

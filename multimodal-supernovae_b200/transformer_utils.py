@@ -70,14 +70,16 @@ class TransformerBlock(nn.Module):
         self.do = nn.Dropout(dropout)
 
     def forward(self, x, mask=None):
-        if self.training and self.do.p > 0:
-            raise NotImplementedError("maven_b200: dropout>0 in train mode is not available on the per-block path")
+        p = float(self.do.p) if self.training else 0.0
+        seed = ops.next_dropout_seed(self) if p > 0.0 else 0    # sites: 0 after norm1, 1 after norm2 (:112,115)
         prec = _prec_of(self)
         a = self.attention.heads_out(x, mask)
         u = self.attention.unifyheads
         x = ops.LinearResLNFn.apply(a, u.weight, u.bias, x, self.norm1.weight, self.norm1.bias, self.norm1.eps, prec)
-        return ops.FFNResLNFn.apply(x, self.ff[0].weight, self.ff[0].bias, self.ff[2].weight, self.ff[2].bias,
-                                    self.norm2.weight, self.norm2.bias, self.norm2.eps, prec)
+        x = ops.dropout(x, p, seed, 0)
+        x = ops.FFNResLNFn.apply(x, self.ff[0].weight, self.ff[0].bias, self.ff[2].weight, self.ff[2].bias,
+                                 self.norm2.weight, self.norm2.bias, self.norm2.eps, prec)
+        return ops.dropout(x, p, seed, 1)
 
 
 class Transformer(nn.Module):
@@ -91,8 +93,8 @@ class Transformer(nn.Module):
         self.emb, self.heads, self.depth, self.ff_hidden_mult = emb, heads, depth, ff_hidden_mult
 
     def forward(self, x, mask=None):
-        if self.training and self.do.p > 0:
-            raise NotImplementedError("maven_b200: dropout>0 in train mode is not available on the per-block path")
+        p = float(self.do.p) if self.training else 0.0
+        x = ops.dropout(x, p, ops.next_dropout_seed(self) if p > 0.0 else 0, 0)      # input dropout (:147)
         for tblock in self.tblocks:
             x = tblock(x, mask)
         return x
@@ -168,23 +170,10 @@ class TransformerWithTimeEmbeddings(nn.Module):
     def head_params(self):
         return [self.projection.weight, self.projection.bias]
 
-    def _next_dropout_seed(self) -> int:
-        """A fresh 64-bit seed per training-mode call (the kernels regenerate the masks from it in the backward).  Derived
-        from torch's seed and a call counter, so runs are reproducible under torch.manual_seed; `dropout_seed` pins it."""
-        fixed = getattr(self, "dropout_seed", None)
-        if fixed is not None:
-            return int(fixed) & 0xFFFFFFFFFFFFFFFF
-        self._drop_calls = getattr(self, "_drop_calls", 0) + 1
-        rank = 0
-        if torch.distributed.is_available() and torch.distributed.is_initialized():
-            rank = torch.distributed.get_rank()                     # data-parallel shards draw different masks
-        return (torch.initial_seed() * 0x9E3779B97F4A7C15 + self._drop_calls * 0xD1B54A32D192ED03 + (id(self) % 65521) * 0x2545F491
-                + rank * 0x9FB21C651E98DF25) & 0xFFFFFFFFFFFFFFFF
-
     def make_cfg(self, agg_code: int, enc_dim: int, normalize: bool) -> SeqCfg:
         tr = self.transformer
         p = float(tr.do.p) if self.training else 0.0
-        seed = self._next_dropout_seed() if p > 0.0 else 0
+        seed = ops.next_dropout_seed(self) if p > 0.0 else 0
         return SeqCfg(B=0, T=0, E=tr.emb, H=tr.heads, depth=tr.depth, nband=self.nband, n_out=self.n_out, enc_dim=enc_dim,
                       agg=agg_code, normalize=1 if normalize else 0, prec=_prec_of(self), ff_mult=tr.ff_hidden_mult,
                       ln_eps=1e-5, dropout_p=p, seed=seed)

@@ -174,29 +174,42 @@ def _bn(sd: SD, p: str, x: Tensor, training: bool, stats_out: Optional[SD]) -> T
 
 
 def convmixer(sd: SD, p: str, x: Tensor, *, depth: int, kernel_size: int, patch_size: int,
-              training: bool = True, stats_out: Optional[SD] = None) -> Tensor:
+              training: bool = True, stats_out: Optional[SD] = None, drop_scales: Optional[dict] = None) -> Tensor:
+    """drop_scales (optional): keep factors (0 or 1/(1-p)) of the nn.Dropout layers (src/models_multimodal.py:62-77,85-87),
+    keyed by site: s in 1..2*depth follows BatchNorm s (NCHW feature-map shape), 1+2*depth follows the head's GELU
+    ((B, 1024)).  Dropout parity is defined on a GIVEN mask, like the sequence encoder's."""
+    ds = drop_scales or {}
     dim = sd[p + "net.0.weight"].shape[0]
     x = F.conv2d(x, sd[p + "net.0.weight"], None, stride=patch_size)
     x = _bn(sd, p + "net.2.", F.gelu(x), training, stats_out)
     for d in range(depth):
         q = f"{p}net.{3 + d}."
         y = F.conv2d(x, sd[q + "0.fn.0.weight"], sd[q + "0.fn.0.bias"], groups=dim, padding="same")
-        x = _bn(sd, q + "0.fn.2.", F.gelu(y), training, stats_out) + x
+        y = _bn(sd, q + "0.fn.2.", F.gelu(y), training, stats_out)
+        x = (y * ds[2 * d + 1] if 2 * d + 1 in ds else y) + x
         y = F.conv2d(x, sd[q + "1.weight"], sd[q + "1.bias"])
         x = _bn(sd, q + "3.", F.gelu(y), training, stats_out)
+        if 2 * d + 2 in ds:
+            x = x * ds[2 * d + 2]
     x = x.mean(dim=(2, 3))
     x = F.gelu(F.linear(x, sd[p + "projection.2.weight"], sd[p + "projection.2.bias"]))
+    if 2 * depth + 1 in ds:
+        x = x * ds[2 * depth + 1]
     return F.linear(x, sd[p + "projection.5.weight"], sd[p + "projection.5.bias"])
 
 
 # --------------------------------------------------------------------------------------
 # meta encoder (N4)                          src/models_multimodal.py:295-304, 834-857
 # --------------------------------------------------------------------------------------
-def meta_encoder(sd: SD, classification: Tensor, redshift: Tensor, input_dim: int, num_layers: int) -> Tensor:
+def meta_encoder(sd: SD, classification: Tensor, redshift: Tensor, input_dim: int, num_layers: int,
+                 drop_scales: Optional[Sequence[Tensor]] = None) -> Tensor:
+    """drop_scales (optional): one keep-factor tensor (B, hidden) per hidden layer (Linear -> ReLU -> Dropout, :842-853)."""
     x = torch.cat([sd["class_emb.weight"][classification.long()],
                    redshift.unsqueeze(1).repeat(1, input_dim // 2)], dim=-1)
     for i in range(num_layers):
         x = torch.relu(F.linear(x, sd[f"meta_encoder.layers.{3 * i}.weight"], sd[f"meta_encoder.layers.{3 * i}.bias"]))
+        if drop_scales is not None:
+            x = x * drop_scales[i]
     j = 3 * num_layers
     return F.linear(x, sd[f"meta_encoder.layers.{j}.weight"], sd[f"meta_encoder.layers.{j}.bias"])
 

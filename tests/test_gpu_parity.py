@@ -457,3 +457,100 @@ def test_seq_encoder_dropout_given_mask(L, prec):
     assert relerr(y, yr) < tol_f
     for k, p_ in enc.named_parameters():
         assert relerr(p_.grad, sdg[k].grad) < tol_g, k
+
+
+def _site_scale(L, seed, site, p, rows, cols):
+    buf = torch.empty(rows, cols, device=dev())
+    assert L.mvn_dropout_scale(seed, site, p, rows, cols, P(buf), S()) == 0
+    return buf.cpu()
+
+
+def test_convmixer_dropout_given_mask(L):
+    """ConvMixer's nn.Dropout layers (after every mixer BatchNorm and after the head's GELU, src/models_multimodal.py:62-77,
+    85-87) run in-kernel from counter-based masks; the masks are read back with mvn_dropout_scale, reshaped to NCHW and
+    injected into the oracle.  Forward, parameter gradients and running statistics must then agree."""
+    from maven_b200.models_multimodal import ConvMixer
+    torch.manual_seed(13)
+    dim, depth, B, pd, seed = 32, 2, 70, 0.25, 0xBEEF1234CAFE
+    cm = ConvMixer(dim=dim, depth=depth, channels=3, kernel_size=5, patch_size=10, n_out=32, dropout_prob=pd)
+    sdg = {k: (v.detach().double().requires_grad_() if v.is_floating_point() else v.clone()) for k, v in cm.state_dict().items()}
+    img = torch.rand(B, 3, 60, 60)
+    w = torch.randn(B, 32)
+    cm = cm.to(dev()).train()
+    cm.dropout_seed = seed
+    y = cm(img.to(dev()))
+    (y * w.to(dev())).sum().backward()
+    y2 = cm(img.to(dev()))
+    assert torch.equal(y, y2)
+    cm.dropout_seed = seed + 1
+    assert not torch.equal(y, cm(img.to(dev())))
+    masks = {}
+    for s in range(1, 2 * depth + 1):
+        m = _site_scale(L, seed, s, pd, B * 36, dim)                       # rows = (b, py, px), cols = channel
+        masks[s] = m.view(B, 6, 6, dim).permute(0, 3, 1, 2).double()
+    masks[2 * depth + 1] = _site_scale(L, seed, 2 * depth + 1, pd, B, 1024).double()
+    keep = torch.cat([m.flatten() for m in masks.values()]).ne(0).float().mean().item()
+    assert abs(keep - (1 - pd)) < 0.01
+    yr = O.convmixer(sdg, "", img.double(), depth=depth, kernel_size=5, patch_size=10, training=True, drop_scales=masks)
+    (yr * w.double()).sum().backward()
+    assert relerr(y, yr) < 2 * TOL
+    for k, p_ in cm.named_parameters():
+        assert relerr(p_.grad, sdg[k].grad) < GTOL or (p_.grad.cpu() - sdg[k].grad).abs().max() < 1e-6, k
+    # eval mode ignores dropout
+    cm.eval()
+    with torch.no_grad():
+        ye = cm(img.to(dev()))
+    cm.dropout_prob = 0.0
+    with torch.no_grad():
+        assert torch.equal(ye, cm(img.to(dev())))
+
+
+def test_mlp_dropout_given_mask(L):
+    """Meta-encoder MLP (src/models_multimodal.py:834-857): Linear -> ReLU -> Dropout stacks with the library's mask."""
+    from maven_b200.models_multimodal import MLP
+    torch.manual_seed(17)
+    B, pd, seed = 50, 0.3, 0x5EED5EED
+    mlp = MLP(input_dim=16, hidden_dim=64, output_dim=128, num_layers=2, dropout=pd)
+    sd = {"meta_encoder." + k: v.detach().double().requires_grad_() for k, v in mlp.state_dict().items()}
+    x = torch.randn(B, 16)
+    w = torch.randn(B, 128)
+    mlp = mlp.to(dev()).train()
+    mlp.dropout_seed = seed
+    y = mlp(x.to(dev()))
+    (y * w.to(dev())).sum().backward()
+    scales = [_site_scale(L, seed, i, pd, B, 64).double() for i in range(2)]
+    h = x.double()
+    for i in range(2):
+        h = torch.relu(torch.nn.functional.linear(h, sd[f"meta_encoder.layers.{3 * i}.weight"], sd[f"meta_encoder.layers.{3 * i}.bias"])) * scales[i]
+    yr = torch.nn.functional.linear(h, sd["meta_encoder.layers.6.weight"], sd["meta_encoder.layers.6.bias"])
+    (yr * w.double()).sum().backward()
+    assert relerr(y, yr) < TOL
+    for k, p_ in mlp.named_parameters():
+        assert relerr(p_.grad, sd["meta_encoder." + k].grad) < GTOL, k
+
+
+def test_transformer_block_dropout_given_mask(L):
+    """Stand-alone Transformer (input dropout) and TransformerBlock (dropout after both LayerNorms), :112,115,147."""
+    from maven_b200.transformer_utils import Transformer
+    torch.manual_seed(19)
+    B, T, E, pd = 3, 40, 32, 0.2
+    tr = Transformer(emb=E, heads=2, depth=2, dropout=pd)
+    sdg = {k: v.detach().double().requires_grad_() for k, v in tr.state_dict().items()}
+    x = torch.randn(B, T, E)
+    mask = torch.rand(B, T) > 0.3
+    mask[:, 0] = True
+    w = torch.randn(B, T, E)
+    tr = tr.to(dev()).train()
+    tr.dropout_seed = 101
+    for i, blk in enumerate(tr.tblocks):
+        blk.dropout_seed = 202 + i
+    y = tr(x.to(dev()), mask.to(dev()))
+    (y * w.to(dev())).sum().backward()
+    scales = [_site_scale(L, 101, 0, pd, B * T, E).view(B, T, E).double()]
+    for i in range(2):
+        scales += [_site_scale(L, 202 + i, 0, pd, B * T, E).view(B, T, E).double(), _site_scale(L, 202 + i, 1, pd, B * T, E).view(B, T, E).double()]
+    yr = O.transformer(sdg, "", x.double(), mask, 2, 2, scales)
+    (yr * w.double()).sum().backward()
+    assert relerr(y, yr) < 2 * TOL
+    for k, p_ in tr.named_parameters():
+        assert relerr(p_.grad, sdg[k].grad) < GTOL, k

@@ -149,3 +149,48 @@ def test_retrieval_ranks_matches_argsort_loop():
         cs = torch.nn.functional.cosine_similarity(e1, e2[j][None], dim=-1)
         order = torch.argsort(cs, descending=True)
         assert int((order == j).nonzero()[0, 0]) == int(r[j])
+
+
+class _GivenMask(torch.nn.Module):
+    """Stands in for nn.Dropout: multiplies by a given keep-factor tensor."""
+
+    def __init__(self, scale):
+        super().__init__()
+        self.scale = scale
+
+    def forward(self, x):
+        return x * self.scale
+
+
+def test_convmixer_given_dropout_masks_match_torch_layers():
+    """The oracle's drop_scales path == the reference's nn.Sequential layout (src/models_multimodal.py:52-89, rebuilt here
+    from stock torch layers) with every nn.Dropout replaced by the same given mask."""
+    import torch.nn as nn
+    torch.manual_seed(5)
+    dim, depth, k, p, B, pd = 16, 2, 5, 10, 6, 0.3
+    net = nn.Sequential(nn.Conv2d(3, dim, p, stride=p, bias=False), nn.GELU(), nn.BatchNorm2d(dim))
+    masks = {}
+    for d in range(depth):
+        masks[2 * d + 1] = (torch.rand(B, dim, 6, 6) > pd).double() / (1 - pd)
+        masks[2 * d + 2] = (torch.rand(B, dim, 6, 6) > pd).double() / (1 - pd)
+
+        class Res(nn.Module):
+            def __init__(self, fn):
+                super().__init__()
+                self.fn = fn
+
+            def forward(self, x):
+                return self.fn(x) + x
+        net.append(nn.Sequential(Res(nn.Sequential(nn.Conv2d(dim, dim, k, groups=dim, padding="same"), nn.GELU(), nn.BatchNorm2d(dim),
+                                                   _GivenMask(masks[2 * d + 1]))),
+                                 nn.Conv2d(dim, dim, 1), nn.GELU(), nn.BatchNorm2d(dim), _GivenMask(masks[2 * d + 2])))
+    masks[2 * depth + 1] = (torch.rand(B, 1024) > pd).double() / (1 - pd)
+    proj = nn.Sequential(nn.AdaptiveAvgPool2d((1, 1)), nn.Flatten(), nn.Linear(dim, 1024), nn.GELU(), _GivenMask(masks[2 * depth + 1]),
+                         nn.Linear(1024, 8))
+    full = nn.ModuleDict({"net": net, "projection": proj}).double().train()
+    img = torch.rand(B, 3, 60, 60, dtype=torch.float64)
+    sd = {k_: v.detach().clone() for k_, v in full.state_dict().items()}
+    ref = full["projection"](full["net"](img))
+    got = O.convmixer(sd, "", img, depth=depth, kernel_size=k, patch_size=p, training=True, drop_scales=masks)
+    assert relerr(got, ref) < 1e-12
+    assert relerr(O.convmixer(sd, "", img, depth=depth, kernel_size=k, patch_size=p, training=True), ref) > 1e-3
