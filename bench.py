@@ -323,17 +323,17 @@ def run_gpu(args):
         flush.fill_(1)
         step(resident)
     torch.cuda.synchronize()
+    L.mvn_prof_enable(0)
     model.concurrent_modalities = concurrent
-    for _ in range(2):
-        step(resident)
-    sync()
     breakdown, prof_tot = {}, {}
     for c, nme in enumerate(names):
         ms, cnt = ctypes.c_double(), ctypes.c_longlong()
         L.mvn_prof_read(c, ctypes.byref(ms), ctypes.byref(cnt))
         breakdown[nme] = {"ms": round(ms.value / args.steps, 4), "launches": cnt.value // args.steps}
         prof_tot[nme] = (ms.value, cnt.value)
-    L.mvn_prof_enable(0)
+    for _ in range(2):
+        step(resident)
+    sync()
     top = max(("gemm", "wgrad", "attn_fwd", "attn_bwd", "row"), key=lambda k: breakdown[k]["ms"])
     ms_t, cnt_t = ctypes.c_double(prof_tot[top][0]), ctypes.c_longlong(prof_tot[top][1])
 
@@ -352,7 +352,8 @@ def run_gpu(args):
     sync()
     wall = time.perf_counter() - wall0
     launches = L.mvn_launch_count() - launches0
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    dev_ms = sum(step_ms)
     clocks = sampler.stop()            # sampled during the throughput region only: NVML queries perturb the sync-per-step e2e loop
 
     # ---- e2e: pinned host batch -> H2D -> step -> D2H loss, everything inside the timed region -----------
@@ -432,7 +433,7 @@ def run_gpu(args):
         "step_tflops": {"padded_equivalent": fl["padded_train"] / (ms_per_step / 1e3) / 1e12, "executed": fl["executed_train"] / (ms_per_step / 1e3) / 1e12,
                         "frac_of_peak_padded": fl["padded_train"] / (ms_per_step / 1e3) / 1e12 / tf},
         "kernel_breakdown_ms": breakdown,
-        "wall_s_timed_region": wall, "loss_last": last,
+        "wall_s_timed_region": wall, "loss_last": last, "step_ms_rank0": [round(x, 3) for x in step_ms],
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu

@@ -163,13 +163,19 @@ __global__ void __launch_bounds__(256) gelu_stats_kernel(const float* __restrict
         stat_part[(size_t)blockIdx.x * 2 * dim + i] = s;
     }
 }
-// stats[i] = sum over CTAs
+// stats[i] = sum over CTAs (one warp per output, fixed lane/shuffle order -> deterministic)
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
 __global__ void stat_reduce_kernel(const double* __restrict__ part, int nblk, int n, double* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= n) return;
     double s = 0.0;
-    for (int b = 0; b < nblk; ++b) s += part[(size_t)b * n + i];
-    out[i] = s;
+    for (int b = lane; b < nblk; b += 32) s += part[(size_t)b * n + i];
+    s = warp_sum_f64(s);
+    if (lane == 0) out[i] = s;
 }
 // batch statistics -> normalisation coefficients (+ running-stat update); stats = [sum a | sum a^2] over `count` values
 __global__ void bn_coeffs_kernel(const double* __restrict__ stats, double count, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -234,28 +240,61 @@ __global__ void dwconv_kernel(const float* __restrict__ x, const float* __restri
         y[i] = acc;
     }
 }
-// depthwise weight/bias gradient partials: partial[s][woff + c*k*k + tap] = sum du[r,c]*x[r+tap,c], [boff + c] = sum du
+// depthwise weight/bias gradient partials: partial[cta][woff + c*k*k + tap] = sum du[r,c]*x[r+tap,c], [boff + c] = sum du.
+// One CTA per slab of samples: the sample's two [P, dim] maps are staged in shared memory (coalesced float4 loads), then
+// thread (c = tid % dim, tg = tid / dim) accumulates its taps {tg, tg+ntg, ...} over the P positions from shared memory.
+// Tap index k*k is the bias column.  Fixed summation order per CTA -> deterministic.
 __global__ void __launch_bounds__(256) dwconv_wgrad_kernel(const float* __restrict__ du, const float* __restrict__ x, int B, int Hp, int Wp, int dim, int k,
                                                            float* __restrict__ partial, size_t pstride, size_t woff, size_t boff) {
-    // thread (c, tap-group): each thread owns channel c = tid % dim and taps t = tid / dim, += 256/dim
+    extern __shared__ __align__(16) float dw_sm[];
+    const int P = Hp * Wp, n = P * dim;
+    float* sdu = dw_sm;
+    float* sx = dw_sm + n;
     const int c = threadIdx.x % dim, tg = threadIdx.x / dim, ntg = blockDim.x / dim;
-    if (tg >= ntg) return;
-    const int h = k / 2, kk = k * k;
-    const int R = B * Hp * Wp;
+    const int h = k / 2, kk = k * k, ntaps = kk + 1;
+    constexpr int TPT = 8;                                   // taps per thread per pass
     float* pp = partial + (size_t)blockIdx.x * pstride;
-    for (int tap = tg; tap <= kk; tap += ntg) {             // tap == kk is the bias column
-        const int ii = tap / k, jj = tap % k;
-        float acc = 0.f;
-        for (int r = blockIdx.x; r < R; r += gridDim.x) {
-            const float g = du[(size_t)r * dim + c];
-            if (tap == kk) { acc += g; continue; }
-            const int px = r % Wp, py = (r / Wp) % Hp;
-            const int yy = py + ii - h, xx = px + jj - h;
-            if (yy < 0 || yy >= Hp || xx < 0 || xx >= Wp) continue;
-            const long long rr = (long long)r + (long long)(yy - py) * Wp + (xx - px);
-            acc = fmaf(g, x[(size_t)rr * dim + c], acc);
+    for (int t0 = 0; t0 < ntaps; t0 += TPT * ntg) {
+        float acc[TPT];
+#pragma unroll
+        for (int j = 0; j < TPT; ++j) acc[j] = 0.f;
+        for (int b = blockIdx.x; b < B; b += gridDim.x) {
+            __syncthreads();
+            const float4* gdu = reinterpret_cast<const float4*>(du + (size_t)b * n);
+            const float4* gx = reinterpret_cast<const float4*>(x + (size_t)b * n);
+            for (int i = threadIdx.x; i < n / 4; i += blockDim.x) {
+                reinterpret_cast<float4*>(sdu)[i] = gdu[i];
+                reinterpret_cast<float4*>(sx)[i] = gx[i];
+            }
+            __syncthreads();
+            if (tg < ntg) {
+#pragma unroll
+                for (int j = 0; j < TPT; ++j) {
+                    const int tap = t0 + tg + j * ntg;
+                    if (tap >= ntaps) continue;
+                    float a = 0.f;
+                    if (tap == kk) {
+                        for (int q = 0; q < P; ++q) a += sdu[q * dim + c];
+                    } else {
+                        const int dy = tap / k - h, dx = tap % k - h;
+                        const int y0 = dy < 0 ? -dy : 0, y1 = dy > 0 ? Hp - dy : Hp;
+                        const int x0 = dx < 0 ? -dx : 0, x1 = dx > 0 ? Wp - dx : Wp;
+                        for (int py = y0; py < y1; ++py)
+                            for (int px = x0; px < x1; ++px)
+                                a = fmaf(sdu[(py * Wp + px) * dim + c], sx[((py + dy) * Wp + px + dx) * dim + c], a);
+                    }
+                    acc[j] += a;
+                }
+            }
         }
-        if (tap == kk) pp[boff + c] = acc; else pp[woff + (size_t)c * kk + tap] = acc;
+        if (tg < ntg) {
+#pragma unroll
+            for (int j = 0; j < TPT; ++j) {
+                const int tap = t0 + tg + j * ntg;
+                if (tap < kk) pp[woff + (size_t)c * kk + tap] = acc[j];
+                else if (tap == kk) pp[boff + c] = acc[j];
+            }
+        }
     }
 }
 __global__ void avgpool_fwd_kernel(const float* __restrict__ z, int B, int P, int dim, float* __restrict__ pooled) {
@@ -310,12 +349,15 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const float* __restri
 }
 // local sums -> stats_out (for the all-reduce) and the parameter gradients dgamma = sum dout*xhat, dbeta = sum dout
 __global__ void bn_bwd_reduce_kernel(const double* __restrict__ part, int nblk, int dim, double* __restrict__ out, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= 2 * dim) return;
     double s = 0.0;
-    for (int b = 0; b < nblk; ++b) s += part[(size_t)b * 2 * dim + i];
-    out[i] = s;
-    if (i < dim) dbeta[i] = (float)s; else dgamma[i - dim] = (float)s;
+    for (int b = lane; b < nblk; b += 32) s += part[(size_t)b * 2 * dim + i];
+    s = warp_sum_f64(s);
+    if (lane == 0) {
+        out[i] = s;
+        if (i < dim) dbeta[i] = (float)s; else dgamma[i - dim] = (float)s;
+    }
 }
 // du = gelu'(u) * scale * (dout - S1/N - xhat*S2/N)
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ a, const float* __restrict__ u,
@@ -392,7 +434,7 @@ extern "C" int mvn_convmixer_fwd_stage(const mvn_conv_cfg* cfg, int stage, const
         gelu_stats_kernel<<<kSlabs, 256, 0, st>>>(bn.u, bn.a, R, dim, c.training ? w.stat_part : nullptr);
         MVN_LAUNCH_CHECK();
         if (c.training) {
-            stat_reduce_kernel<<<cdiv(2 * dim, 128), 128, 0, st>>>(w.stat_part, kSlabs, 2 * dim, bn_stats + (size_t)s * 2 * dim);
+            stat_reduce_kernel<<<cdiv(2 * dim, 8), 256, 0, st>>>(w.stat_part, kSlabs, 2 * dim, bn_stats + (size_t)s * 2 * dim);
             MVN_LAUNCH_CHECK();
         }
         return 0;
@@ -478,7 +520,7 @@ extern "C" int mvn_convmixer_bwd_stage(const mvn_conv_cfg* cfg, int stage, const
         const ConvWs::Bn bn = w.bn(s);
         bn_bwd_stats_kernel<<<kSlabs, 256, 0, st>>>(w.dZ, bn.a, bn.mean, bn.rstd, R, dim, w.stat_part, conv_drop(c, s));
         MVN_LAUNCH_CHECK();
-        bn_bwd_reduce_kernel<<<cdiv(2 * dim, 128), 128, 0, st>>>(w.stat_part, kSlabs, dim, bn_stats_bwd + (size_t)s * 2 * dim, grads + g, grads + b);
+        bn_bwd_reduce_kernel<<<cdiv(2 * dim, 8), 256, 0, st>>>(w.stat_part, kSlabs, dim, bn_stats_bwd + (size_t)s * 2 * dim, grads + g, grads + b);
         MVN_LAUNCH_CHECK();
         return 0;
     };
@@ -529,7 +571,7 @@ extern "C" int mvn_convmixer_bwd_stage(const mvn_conv_cfg* cfg, int stage, const
     const size_t lbase = o.layer0 + (size_t)d * o.layer_stride;
     const float* LP = params + lbase;
     if (s & 1) {    // depthwise conv: input x = z_{s-1}; total grad of x = dYres (residual path) + dwconv^T(dU)
-        dwconv_wgrad_kernel<<<kSlabs, 256, 0, st>>>(w.dU, w.bn(s - 1).z, c.B, Hp, Wp, dim, c.kernel_size, part, ps, lbase + o.dw_w, lbase + o.dw_b);
+        dwconv_wgrad_kernel<<<kSlabs, 256, (size_t)2 * P * dim * sizeof(float), st>>>(w.dU, w.bn(s - 1).z, c.B, Hp, Wp, dim, c.kernel_size, part, ps, lbase + o.dw_w, lbase + o.dw_b);
         MVN_LAUNCH_CHECK();
         dwconv_kernel<<<ew_blocks(n), 256, (size_t)c.kernel_size * c.kernel_size * dim * 4, st>>>(w.dU, LP + o.dw_w, nullptr, w.dYres, w.dZ, c.B, Hp, Wp, dim,
                                                                                                  c.kernel_size, 1);

@@ -21,7 +21,7 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     prec = sys.argv[1] if len(sys.argv) > 1 else "fp32"
-    wl = bench.WORKLOADS["c4"]
+    wl = bench.WORKLOADS[sys.argv[2] if len(sys.argv) > 2 else "c4"]
     n = 64
     gbatch = bench.make_batch(wl, n * world, seed=7)                       # the same global batch on every rank
     shard = [None if v is None else v[rank * n:(rank + 1) * n].to(dev) for v in gbatch]
@@ -48,7 +48,7 @@ def main():
         eg = ((g - g1).norm() / g1.norm()).item()
         tol_l, tol_g = (1e-5, 2e-4) if prec == "fp32" else (1e-3, 1e-2)
         ok = el < tol_l and eg < tol_g
-        print(f"dp_parity world={world} prec={prec}: loss dp={loss.item():.7f} single={l1.item():.7f} rel={el:.2e}; flat-grad rel={eg:.2e} -> {'OK' if ok else 'FAIL'}", flush=True)
+        print(f"dp_parity world={world} prec={prec} workload={sys.argv[2] if len(sys.argv) > 2 else 'c4'}: loss dp={loss.item():.7f} single={l1.item():.7f} rel={el:.2e}; flat-grad rel={eg:.2e} -> {'OK' if ok else 'FAIL'}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
