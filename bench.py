@@ -256,7 +256,7 @@ def run_reference(args):
             "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
                              "sample": f"{args.steps} training steps (fwd+bwd+torch RAdam) at batch {B} of the same workload"},
             "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -273,7 +273,6 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"                      # NCCL's version banner goes to stdout otherwise (ONE JSON line)
         dist.init_process_group("nccl", device_id=dev)
         ops.set_data_parallel_group(dist.group.WORLD)
     L = _lib.lib()
@@ -286,9 +285,7 @@ def run_gpu(args):
     host = make_batch(wl, B, seed=1000 + rank)                 # each rank owns its shard of the global batch
     pinned = [None if v is None else v.pin_memory() for v in host]
     resident = [None if v is None else v.to(dev) for v in host]
-    h2d = sum(v.numel() * v.element_size() for v in (pinned[0:7]) if v is not None)
-    if wl.get("classification"):
-        h2d += pinned[8].numel() * pinned[8].element_size()
+    h2d = sum(v.numel() * v.element_size() for v in pinned if v is not None)      # every tensor of the 9-tuple batch is copied per step
     fl = flops_per_step(wl, host)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
 
@@ -334,10 +331,29 @@ def run_gpu(args):
     for _ in range(2):
         step(resident)
     sync()
+
+    # ---- the product's training step: the whole step as ONE CUDA graph (maven_b200.graph), replayed per batch -------------
+    graphed = None
+    if args.graph:
+        from maven_b200.graph import GraphedTrainStep
+        graphed = GraphedTrainStep(model, opt, resident, group=dist.group.WORLD if world > 1 else None)
+
+        def run_step(batch):                                   # batch None: inputs already resident in the static buffers
+            return graphed(batch)
+        for _ in range(2):
+            run_step(None)
+        sync()
+    else:
+        def run_step(batch):
+            return step(resident if batch is None else batch)
     top = max(("gemm", "wgrad", "attn_fwd", "attn_bwd", "row"), key=lambda k: breakdown[k]["ms"])
     ms_t, cnt_t = ctypes.c_double(prof_tot[top][0]), ctypes.c_longlong(prof_tot[top][1])
 
     # ---- timed region: K steps, device-resident inputs, per-step CUDA events, L2 flushed between steps ----
+    import gc
+    gc.collect()
+    gc.freeze()                                                # a generation-2 collection inside the timed region stalls the host for tens of ms
+    gc.disable()
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = L.mvn_launch_count()
@@ -347,17 +363,21 @@ def run_gpu(args):
     for a, b in ev:
         flush.fill_(1)
         a.record()
-        step(resident)
+        run_step(None)
         b.record()
     sync()
     wall = time.perf_counter() - wall0
     launches = L.mvn_launch_count() - launches0
+    if graphed is not None:
+        launches = graphed.launches_per_replay * args.steps     # kernels inside each replayed graph (counted at capture)
     step_ms = [a.elapsed_time(b) for a, b in ev]
     dev_ms = sum(step_ms)
     clocks = sampler.stop()            # sampled during the throughput region only: NVML queries perturb the sync-per-step e2e loop
 
     # ---- e2e: pinned host batch -> H2D -> step -> D2H loss, everything inside the timed region -----------
     def e2e_step():
+        if graphed is not None:
+            return graphed(pinned).item()                      # pinned host batch -> static device buffers -> replay -> D2H loss
         batch = [None if v is None else v.to(dev, non_blocking=True) for v in pinned]
         return step(batch).item()                              # device->host read of the step's loss
 
@@ -370,14 +390,23 @@ def run_gpu(args):
         last = e2e_step()
     sync()
     e2e_wall = time.perf_counter() - t0
+    gc.enable()
 
     t = torch.tensor([dev_ms, e2e_wall * 1e3, float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms, launches = t[0].item(), t[1].item(), int(t[2].item())
-    if rank != 0:
+    def finish():
+        """Multi-rank runs leave through a hard exit once every rank is done: tearing down a NCCL communicator whose
+        collectives were captured into a still-live CUDA graph can block at interpreter exit."""
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
     hbm, tf, src = peaks()
     ms_per_step = dev_ms / args.steps
@@ -416,6 +445,7 @@ def run_gpu(args):
         "config": {"workload": wl["desc"], "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
                    "dropout": args.dropout, "precision": args.precision,
                    "streams": "one CUDA stream per modality encoder" if concurrent and len(wl["combinations"]) > 1 else "single stream",
+                   "launch": "whole step replayed as one CUDA graph (maven_b200.graph.GraphedTrainStep)" if graphed is not None else "eager launches",
                    "l2": "256 MiB flush written between timed steps; per-step activation working set is GBs (>> 126 MB L2)",
                    "valid_token_fraction": {"lc": float(host[3].float().mean()), "sp": float(host[6].float().mean()) if host[6] is not None else None}},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
@@ -437,12 +467,26 @@ def run_gpu(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    emit(line)
+    finish()
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the process's original stdout; everything else written to fd 1 meanwhile (NCCL's version
+    banner, library chatter) has been routed to stderr by main()."""
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)                                              # C-level writes to stdout (NCCL banner) -> stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -456,6 +500,7 @@ def main():
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
                     help="tf32: tcgen05/mma tensor-core tier (fp32 storage, fp32 accumulate; parity 1e-3); fp32: FFMA tier (parity 1e-5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="enqueue every kernel from Python instead of replaying the captured step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

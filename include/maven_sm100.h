@@ -256,6 +256,15 @@ int mvn_mse_bwd(const float* pred, const float* target, int n, const float* grad
 int mvn_radam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                    float lr, float beta1, float beta2, float eps, float weight_decay,
                    float bias_correction1, float sqrt_bias_correction2, float rect, void* stream);
+/* CUDA-graph form of the same update: the step count lives on the device (`step_dev`, incremented by this call) and the
+ * step-dependent scalars (bias corrections, rectification) are computed from it on the device into `scalars_dev[3]`, so a
+ * captured graph performs step t+1's update at its next replay.  All `n` elements share one step count. */
+int mvn_radam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, uint32_t* step_dev, float* scalars_dev, void* stream);
+/* Registers a device-resident step counter (or NULL) that every dropout site mixes into its mask hash, in addition to the
+ * per-call seed: a CUDA graph freezes the seed argument, the counter (advanced by mvn_radam_step_dev) still changes the masks
+ * from replay to replay.  mvn_dropout_scale reads the same counter, so masks stay reproducible for tests. */
+void mvn_set_step_counter(const uint32_t* dev_counter);
 
 /* N3: retrieval rank of the true partner, count_i[cos(e1_i,e2_j) > cos(e1_j,e2_j)].  src/utils.py:380-426. */
 int mvn_retrieval_ranks(const float* e1, const float* e2, int N, int D, int32_t* ranks, void* stream);

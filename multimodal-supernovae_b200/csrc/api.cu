@@ -28,6 +28,8 @@ bool pdl_enabled() {
     if (v < 0) { const char* e = getenv("MVN_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
     return v == 1;
 }
+static const uint32_t* g_step_ctr = nullptr;
+const uint32_t* step_counter() { return g_step_ctr; }
 static long long g_launches = 0;
 void note_launch() { ++g_launches; }
 
@@ -69,6 +71,7 @@ extern "C" int mvn_prof_read(int cls, double* total_ms, long long* count) {
     g_prof[cls].clear();
     return 0;
 }
+extern "C" void mvn_set_step_counter(const uint32_t* dev_counter) { mvn::g_step_ctr = dev_counter; }
 extern "C" long long mvn_launch_count(void) { return mvn::g_launches; }
 
 extern "C" const char* mvn_last_error(void) { return mvn::g_err; }

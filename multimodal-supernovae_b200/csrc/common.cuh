@@ -117,10 +117,13 @@ struct DropCfg {
     uint32_t thresh = 0;     // P(drop) = thresh / 2^32
     float scale = 1.0f;      // 1 / (1 - p) on kept elements
     uint32_t s0 = 0, s1 = 0; // seed words (already mixed with the site id)
+    const uint32_t* ctr = nullptr;   // optional device step counter mixed into every row key (mvn_set_step_counter): lets a
+                                     // CUDA-graph replay, whose kernel arguments are frozen, draw a fresh mask every step
 };
 // Two-level hash: a strong per-row key (computed once per row) and a cheap per-element mix of (rowkey, col).
 __device__ __forceinline__ uint32_t drop_rowkey(const DropCfg& d, uint32_t row) {
     uint32_t h = row ^ d.s0;
+    if (d.ctr) h += __ldg(d.ctr) * 0x9E3779B9u;
     h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
     return h ^ d.s1;
 }
@@ -129,9 +132,11 @@ __device__ __forceinline__ float drop_scale(const DropCfg& d, uint32_t rowkey, u
     h ^= h >> 15; h *= 0x2c1b3c6du; h ^= h >> 12; h *= 0x297a2d39u; h ^= h >> 15;
     return h >= d.thresh ? d.scale : 0.f;
 }
+const uint32_t* step_counter();     // api.cu: device pointer registered with mvn_set_step_counter (nullptr = none)
 static inline DropCfg make_drop(float p, uint64_t seed, uint32_t site) {
     DropCfg d;
     if (!(p > 0.f)) return d;
+    d.ctr = step_counter();
     const double t = (double)p * 4294967296.0;
     d.thresh = t >= 4294967295.0 ? 4294967295u : (uint32_t)t;
     if (d.thresh == 0) d.thresh = 1;

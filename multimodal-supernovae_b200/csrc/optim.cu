@@ -21,6 +21,37 @@ __global__ void __launch_bounds__(256) radam_kernel(float* __restrict__ p, const
     }
 }
 
+// Device-side step bookkeeping for CUDA-graph replays (kernel arguments are frozen in a graph, the step count is not):
+// ++*step, then the step-dependent RAdam scalars in double precision -> scal = {bc1, sqrt(bc2), rect (<0: not rectified)}.
+__global__ void radam_tick_kernel(uint32_t* __restrict__ step, float* __restrict__ scal, double beta1, double beta2) {
+    const uint32_t st = *step + 1u;
+    *step = st;
+    const double b1t = pow(beta1, (double)st), b2t = pow(beta2, (double)st);
+    const double bc1 = 1.0 - b1t, bc2 = 1.0 - b2t;
+    const double rho_inf = 2.0 / (1.0 - beta2) - 1.0;
+    const double rho_t = rho_inf - 2.0 * (double)st * b2t / bc2;
+    double rect = -1.0;
+    if (rho_t > 5.0) rect = sqrt((rho_t - 4.0) * (rho_t - 2.0) * rho_inf / ((rho_inf - 4.0) * (rho_inf - 2.0) * rho_t));
+    scal[0] = (float)bc1; scal[1] = (float)sqrt(bc2); scal[2] = (float)rect;
+}
+__global__ void __launch_bounds__(256) radam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                                        long long n, float lr, float beta1, float beta2, float eps, float wd,
+                                                        const float* __restrict__ scal) {
+    const float bc1 = scal[0], sqrt_bc2 = scal[1], rect = scal[2];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float pi = p[i];
+        float gi = g[i];
+        if (wd != 0.f) gi = fmaf(wd, pi, gi);
+        const float mi = m[i] + (gi - m[i]) * (1.0f - beta1);
+        const float vi = fmaf(v[i], beta2, gi * gi * (1.0f - beta2));
+        m[i] = mi; v[i] = vi;
+        const float mhat = mi / bc1;
+        float step = mhat * lr;
+        if (rect >= 0.f) step *= (sqrt_bc2 / (sqrtf(vi) + eps)) * rect;
+        p[i] = pi - step;
+    }
+}
+
 // one warp per sample: numerically stable log-softmax at the label
 __global__ void ce_rows_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, const float* __restrict__ cw, int B, int C,
                                float* __restrict__ wnll, float* __restrict__ wsum) {
@@ -125,6 +156,19 @@ extern "C" int mvn_radam_step(float* param, const float* grad, float* exp_avg, f
     const long long blocks = (n + 255) / 256;
     radam_kernel<<<(int)(blocks < 2368 ? blocks : 2368), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                                                        weight_decay, bias_correction1, sqrt_bias_correction2, rect);
+    MVN_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mvn_radam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                                  float beta2, float eps, float weight_decay, uint32_t* step_dev, float* scalars_dev, void* stream) {
+    MVN_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && step_dev && scalars_dev, "radam_step_dev: bad arguments");
+    ProfScope prof(PROF_OPTIM, (cudaStream_t)stream);
+    radam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, scalars_dev, (double)beta1, (double)beta2);
+    MVN_LAUNCH_CHECK();
+    const long long blocks = (n + 255) / 256;
+    radam_dev_kernel<<<(int)(blocks < 2368 ? blocks : 2368), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                                                           weight_decay, scalars_dev);
     MVN_LAUNCH_CHECK();
     return 0;
 }

@@ -277,6 +277,19 @@ def next_dropout_seed(module) -> int:
             + rank * 0x9FB21C651E98DF25) & 0xFFFFFFFFFFFFFFFF
 
 
+_STEP_COUNTER = None       # keeps the registered device counter alive for as long as the library points at it
+
+
+def set_step_counter(counter: Optional[torch.Tensor]):
+    """Registers a 1-element int32 CUDA tensor (or None) as the library's device step counter (mvn_set_step_counter):
+    every dropout site mixes its value into the mask hash, which is what varies the masks across CUDA-graph replays."""
+    global _STEP_COUNTER
+    if counter is not None and not (counter.is_cuda and counter.dtype == torch.int32 and counter.numel() == 1):
+        raise TypeError("maven_b200: the step counter must be a 1-element int32 CUDA tensor")
+    lib().mvn_set_step_counter(None if counter is None else ctypes.c_void_p(counter.data_ptr()))
+    _STEP_COUNTER = counter
+
+
 class DropoutFn(torch.autograd.Function):
     """nn.Dropout over the last dimension's rows with the library's counter-based mask (mvn_dropout_apply); the backward
     regenerates the mask from (seed, site)."""

@@ -27,6 +27,44 @@ class FusedRAdam(torch.optim.Optimizer):
         self._steps: Optional[list] = None          # per-parameter step counts (torch skips params whose grad is None)
         self._gstage: Optional[torch.Tensor] = None
 
+    # ---- CUDA-graph support (maven_b200.graph.GraphedTrainStep) ------------------------------------------------
+    def snapshot(self):
+        return (None if self._m is None else self._m.clone(), None if self._v is None else self._v.clone(),
+                None if self._steps is None else list(self._steps))
+
+    def restore(self, snap):
+        m, v, steps = snap
+        if m is None:
+            self._m = self._v = self._steps = None
+        else:
+            self._m.copy_(m); self._v.copy_(v); self._steps = list(steps)
+
+    def enable_device_step(self):
+        """From now on step() keeps the step count on the device and computes the step-dependent scalars there
+        (mvn_radam_step_dev), so that it can be captured in a CUDA graph; the same counter re-seeds the dropout masks."""
+        g: ops.FlatParams = self.model.flat_group()
+        flat = g.ensure()
+        self._ensure_state(g, flat)
+        start = max(self._steps) if self._steps else 0
+        if self._steps and min(self._steps) != start:
+            raise RuntimeError("FusedRAdam: device-side stepping needs every parameter at the same step count")
+        self._step_dev = torch.full((1,), start, dtype=torch.int32, device=flat.device)
+        self._scal_dev = torch.zeros(4, dtype=torch.float32, device=flat.device)
+        ops.set_step_counter(self._step_dev)
+
+    def disable_device_step(self):
+        """Back to host-side stepping (eager mode); the host mirror of the step count carries on from the device's."""
+        if getattr(self, "_step_dev", None) is not None:
+            n = int(self._step_dev.item())
+            self._steps = [n] * len(self._steps)
+            if ops._STEP_COUNTER is self._step_dev:
+                ops.set_step_counter(None)
+            self._step_dev = self._scal_dev = None
+
+    def note_graph_replay(self):
+        if self._steps is not None:
+            self._steps = [s + 1 for s in self._steps]
+
     def _ensure_state(self, g: ops.FlatParams, flat: torch.Tensor):
         if self._m is None or self._m.numel() != g.total or self._m.device != flat.device:
             self._m = torch.zeros_like(flat)
@@ -60,6 +98,18 @@ class FusedRAdam(torch.optim.Optimizer):
                 runs.append([o, o + n, st])
         lr, (b1, b2), eps, wd = grp["lr"], grp["betas"], grp["eps"], grp["weight_decay"]
         stream = ops._stream()
+        if getattr(self, "_step_dev", None) is not None:
+            if len(runs) != 1 or runs[0][0] != 0 or runs[0][1] != g.total:
+                raise RuntimeError("FusedRAdam: device-side stepping needs a gradient for every parameter at every step")
+            for k in range(len(self._steps)):
+                self._steps[k] -= 1                  # the device counter is the truth; note_graph_replay() advances the mirror
+            check(L.mvn_radam_step_dev(ctypes.c_void_p(flat.data_ptr()), ctypes.c_void_p(gbuf.data_ptr()), ctypes.c_void_p(self._m.data_ptr()),
+                                       ctypes.c_void_p(self._v.data_ptr()), g.total, lr, b1, b2, eps, wd,
+                                       ctypes.c_void_p(self._step_dev.data_ptr()), ctypes.c_void_p(self._scal_dev.data_ptr()), stream), "radam_step_dev")
+            ops._count(2)
+            if not torch.cuda.is_current_stream_capturing():
+                self.note_graph_replay()             # an eager call in device-step mode really executed a step
+            return loss
         for o0, o1, st in runs:
             bc1 = 1.0 - b1 ** st
             bc2 = 1.0 - b2 ** st
