@@ -77,11 +77,119 @@ __device__ __forceinline__ void load_afrag(float (*a)[4], const float* __restric
     }
 }
 
+// ---- operand relabelling -------------------------------------------------------------------------------------------
+// An MMA's contraction slots and output columns can be assigned to head dimensions in any order as long as both operands
+// (resp. the consumer of the accumulator) agree.  Two assignments make every shared-memory fragment load a vector load:
+//   pi    (contraction over the head dim, "K-form" B operand = row j of K / V / Q / dO):  slot (ks, t) <-> dim t*(HD/4) + 2ks,
+//         slot (ks, t+4) <-> dim t*(HD/4) + 2ks + 1   => lane t reads the HD/4 contiguous floats [t*HD/4, (t+1)*HD/4) of row j;
+//   sigma (output over the head dim, "V-form" B operand = rows 2t, 2t+1 of V / K / dO / Q):  column (nt, g) <-> dim g*(HD/8) + nt
+//         => lane g reads the HD/8 contiguous floats [g*HD/8, (g+1)*HD/8) of each of its two rows, and the accumulator
+//         fragment of lane t covers the contiguous dims [2t*HD/8, (2t+2)*HD/8) of rows g and g+8.
+template <int HD>
+__device__ __forceinline__ void lds_vec(float* dst, const float* src);       // HD/4 floats (K-form)
+template <>
+__device__ __forceinline__ void lds_vec<8>(float* dst, const float* src) { const float2 v = *reinterpret_cast<const float2*>(src); dst[0] = v.x; dst[1] = v.y; }
+template <>
+__device__ __forceinline__ void lds_vec<16>(float* dst, const float* src) { const float4 v = *reinterpret_cast<const float4*>(src); dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w; }
+template <int HD>
+__device__ __forceinline__ void lds_half(float* dst, const float* src);      // HD/8 floats (V-form)
+template <>
+__device__ __forceinline__ void lds_half<8>(float* dst, const float* src) { dst[0] = *src; }
+template <>
+__device__ __forceinline__ void lds_half<16>(float* dst, const float* src) { const float2 v = *reinterpret_cast<const float2*>(src); dst[0] = v.x; dst[1] = v.y; }
+
+// A-operand fragments under pi (16 rows starting at row0) straight from global memory; rows >= limit read as 0.
+template <int HD>
+__device__ __forceinline__ void load_afrag_pi(float (*a)[4], const float* __restrict__ src, size_t ld, int col, int row0, int limit, float mul, int g, int t) {
+    constexpr int W = HD / 4;
+    float lo[W], hi[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) lo[i] = hi[i] = 0.f;
+    const int r_lo = row0 + g, r_hi = row0 + g + 8;
+    if (r_lo < limit) {
+        const float* p = src + (size_t)r_lo * ld + col + t * W;
+        if constexpr (W == 4) { const float4 v = __ldg(reinterpret_cast<const float4*>(p)); lo[0] = v.x; lo[1] = v.y; lo[2] = v.z; lo[3] = v.w; }
+        else { const float2 v = __ldg(reinterpret_cast<const float2*>(p)); lo[0] = v.x; lo[1] = v.y; }
+    }
+    if (r_hi < limit) {
+        const float* p = src + (size_t)r_hi * ld + col + t * W;
+        if constexpr (W == 4) { const float4 v = __ldg(reinterpret_cast<const float4*>(p)); hi[0] = v.x; hi[1] = v.y; hi[2] = v.z; hi[3] = v.w; }
+        else { const float2 v = __ldg(reinterpret_cast<const float2*>(p)); hi[0] = v.x; hi[1] = v.y; }
+    }
+#pragma unroll
+    for (int ks = 0; ks < HD / 8; ++ks) {
+        a[ks][0] = tf32r(lo[2 * ks] * mul); a[ks][1] = tf32r(hi[2 * ks] * mul);
+        a[ks][2] = tf32r(lo[2 * ks + 1] * mul); a[ks][3] = tf32r(hi[2 * ks + 1] * mul);
+    }
+}
+// like load_slice, but rows up to the next multiple of 32 are zero-filled (branch-free 32-key blocks)
+template <int HD>
+__device__ __forceinline__ void load_slice32(float* dst, const float* __restrict__ src, size_t ld, int col, int row0, int cnt, float mul) {
+    constexpr int LD = HD + 4;
+    const int pad = (cnt + 31) & ~31;
+    for (int idx = threadIdx.x; idx < pad * (HD / 4); idx += ATC_THREADS) {
+        const int j = idx / (HD / 4), d = (idx % (HD / 4)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < cnt) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)(row0 + j) * ld + col + d));
+        *reinterpret_cast<float4*>(dst + j * LD + d) = make_float4(tf32r(v.x * mul), tf32r(v.y * mul), tf32r(v.z * mul), tf32r(v.w * mul));
+    }
+}
+
+// One block of NT key tiles (8 keys each) of the streaming softmax, no per-tile guards: K/V rows past the sequence end are
+// zero in shared memory and only the block that straddles the end (`tail`) masks its scores.
+template <int HD, int NT>
+__device__ __forceinline__ void fwd_block(const float* __restrict__ Ks, const float* __restrict__ Vs, int kb, int kn, const float (*qa)[4],
+                                          float (*o)[4], float& m_lo, float& m_hi, float& l_lo, float& l_hi, int g, int t) {
+    constexpr int LD = HD + 4, KS = HD / 8, W = HD / 4;
+    float s[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        float kf[W];
+        lds_vec<HD>(kf, Ks + (kb + j * 8 + g) * LD + t * W);
+        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) mma_tf32(s[j], qa[ks], kf[2 * ks], kf[2 * ks + 1]);
+    }
+    if (kb + NT * 8 > kn) {
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int kc = kb + j * 8 + 2 * t;
+            if (kc >= kn) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+            if (kc + 1 >= kn) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+        }
+    }
+    float bm_lo = fmaxf(s[0][0], s[0][1]), bm_hi = fmaxf(s[0][2], s[0][3]);
+#pragma unroll
+    for (int j = 1; j < NT; ++j) {
+        bm_lo = fmaxf(bm_lo, fmaxf(s[j][0], s[j][1]));
+        bm_hi = fmaxf(bm_hi, fmaxf(s[j][2], s[j][3]));
+    }
+    bm_lo = quad_max(bm_lo); bm_hi = quad_max(bm_hi);          // finite: key kb < kn is always live
+    const float mn_lo = fmaxf(m_lo, bm_lo), mn_hi = fmaxf(m_hi, bm_hi);
+    const float c_lo = ex2(m_lo - mn_lo), c_hi = ex2(m_hi - mn_hi);
+    m_lo = mn_lo; m_hi = mn_hi;
+    l_lo *= c_lo; l_hi *= c_hi;
+#pragma unroll
+    for (int i = 0; i < KS; ++i) { o[i][0] *= c_lo; o[i][1] *= c_lo; o[i][2] *= c_hi; o[i][3] *= c_hi; }
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        const float p0 = ex2(s[j][0] - mn_lo), p1 = ex2(s[j][1] - mn_lo);
+        const float p2 = ex2(s[j][2] - mn_hi), p3 = ex2(s[j][3] - mn_hi);
+        l_lo += p0 + p1; l_hi += p2 + p3;
+        const float pa[4] = {tf32r(p0), tf32r(p2), tf32r(p1), tf32r(p3)};      // k=t <-> key 2t, k=t+4 <-> key 2t+1
+        float v0[KS], v1[KS];
+        lds_half<HD>(v0, Vs + (kb + j * 8 + 2 * t) * LD + g * KS);
+        lds_half<HD>(v1, Vs + (kb + j * 8 + 2 * t + 1) * LD + g * KS);
+#pragma unroll
+        for (int nt = 0; nt < KS; ++nt) mma_tf32(o[nt], pa, v0[nt], v1[nt]);
+    }
+}
+
 template <int HD>
 __global__ void __launch_bounds__(ATC_THREADS) attn_fwd_mma_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ cu,
                                                                    float* __restrict__ out, float* __restrict__ lse, int E, int H, float scale) {
     pdl_trigger();
-    constexpr int LD = HD + 4;
+    constexpr int LD = HD + 4, KS = HD / 8;
     __shared__ __align__(16) float Ks[CH * LD];
     __shared__ __align__(16) float Vs[CH * LD];
     const int b = blockIdx.x / H, h = blockIdx.x % H;
@@ -96,77 +204,40 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_fwd_mma_kernel(const float* 
     for (int rd = 0; rd < nrounds; ++rd) {
         const int q0 = rd * 64 + warp * 16;
         const bool active = q0 < n;
-        float qa[HD / 8][4];
-        load_afrag<HD>(qa, base, ld, h * HD, q0, n, scale * LOG2E, g, t);      // scores come out in log2 units
-        float o[HD / 8][4];
+        float qa[KS][4];
+        load_afrag_pi<HD>(qa, base, ld, h * HD, q0, n, scale * LOG2E, g, t);      // scores come out in log2 units
+        float o[KS][4];
 #pragma unroll
-        for (int i = 0; i < HD / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+        for (int i = 0; i < KS; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
         float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
 
         for (int c = 0; c < nchunks; ++c) {
             const int k0c = c * CH, kn = min(CH, n - k0c);
             if (nchunks > 1 || rd == 0) {
                 __syncthreads();
-                load_slice<HD>(Ks, base, ld, E + h * HD, k0c, kn, 1.0f);
-                load_slice<HD>(Vs, base, ld, 2 * E + h * HD, k0c, kn, 1.0f);
+                load_slice32<HD>(Ks, base, ld, E + h * HD, k0c, kn, 1.0f);
+                load_slice32<HD>(Vs, base, ld, 2 * E + h * HD, k0c, kn, 1.0f);
                 __syncthreads();
             }
             if (!active) continue;
-            for (int kb = 0; kb < kn; kb += 64) {
-                float s[8][4];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int key0 = kb + j * 8;
-                    s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-                    if (key0 < kn) {
-#pragma unroll
-                        for (int ks = 0; ks < HD / 8; ++ks)
-                            mma_tf32(s[j], qa[ks], Ks[(key0 + g) * LD + ks * 8 + t], Ks[(key0 + g) * LD + ks * 8 + t + 4]);
-                    }
-                }
-                if (kb + 64 > kn) {                      // only the last block of a sequence has keys to mask
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int kc = kb + j * 8 + 2 * t;
-                        if (kc >= kn) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
-                        if (kc + 1 >= kn) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
-                    }
-                }
-                float bm_lo = -INFINITY, bm_hi = -INFINITY;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    bm_lo = fmaxf(bm_lo, fmaxf(s[j][0], s[j][1]));
-                    bm_hi = fmaxf(bm_hi, fmaxf(s[j][2], s[j][3]));
-                }
-                bm_lo = quad_max(bm_lo); bm_hi = quad_max(bm_hi);          // finite: key kb < kn is always live
-                const float mn_lo = fmaxf(m_lo, bm_lo), mn_hi = fmaxf(m_hi, bm_hi);
-                const float c_lo = ex2(m_lo - mn_lo), c_hi = ex2(m_hi - mn_hi);
-                m_lo = mn_lo; m_hi = mn_hi;
-                l_lo *= c_lo; l_hi *= c_hi;
-#pragma unroll
-                for (int i = 0; i < HD / 8; ++i) { o[i][0] *= c_lo; o[i][1] *= c_lo; o[i][2] *= c_hi; o[i][3] *= c_hi; }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int key0 = kb + j * 8;
-                    if (key0 >= kn) break;
-                    const float p0 = ex2(s[j][0] - mn_lo), p1 = ex2(s[j][1] - mn_lo);
-                    const float p2 = ex2(s[j][2] - mn_hi), p3 = ex2(s[j][3] - mn_hi);
-                    l_lo += p0 + p1; l_hi += p2 + p3;
-                    const float pa[4] = {tf32r(p0), tf32r(p2), tf32r(p1), tf32r(p3)};      // k=t <-> key 2t, k=t+4 <-> key 2t+1
-#pragma unroll
-                    for (int nt = 0; nt < HD / 8; ++nt)
-                        mma_tf32(o[nt], pa, Vs[(key0 + 2 * t) * LD + nt * 8 + g], Vs[(key0 + 2 * t + 1) * LD + nt * 8 + g]);
-                }
-            }
+            const int kpad = (kn + 31) & ~31;
+            int kb = 0;
+            for (; kb + 64 <= kpad; kb += 64) fwd_block<HD, 8>(Ks, Vs, kb, kn, qa, o, m_lo, m_hi, l_lo, l_hi, g, t);
+            if (kb < kpad) fwd_block<HD, 4>(Ks, Vs, kb, kn, qa, o, m_lo, m_hi, l_lo, l_hi, g, t);
         }
         if (!active) continue;
         l_lo = quad_sum(l_lo); l_hi = quad_sum(l_hi);
         const float i_lo = 1.0f / l_lo, i_hi = 1.0f / l_hi;
         const int q_lo = q0 + g, q_hi = q0 + g + 8;
-#pragma unroll
-        for (int nt = 0; nt < HD / 8; ++nt) {
-            if (q_lo < n) *reinterpret_cast<float2*>(out + (size_t)(r0 + q_lo) * E + h * HD + nt * 8 + 2 * t) = make_float2(o[nt][0] * i_lo, o[nt][1] * i_lo);
-            if (q_hi < n) *reinterpret_cast<float2*>(out + (size_t)(r0 + q_hi) * E + h * HD + nt * 8 + 2 * t) = make_float2(o[nt][2] * i_hi, o[nt][3] * i_hi);
+        // accumulator columns under sigma: lane t holds dims [2t*KS, 2t*KS + 2*KS) of rows g (c0,c1) and g+8 (c2,c3)
+        float* o_lo = out + (size_t)(r0 + q_lo) * E + h * HD + 2 * t * KS;
+        float* o_hi = out + (size_t)(r0 + q_hi) * E + h * HD + 2 * t * KS;
+        if constexpr (KS == 2) {
+            if (q_lo < n) *reinterpret_cast<float4*>(o_lo) = make_float4(o[0][0] * i_lo, o[1][0] * i_lo, o[0][1] * i_lo, o[1][1] * i_lo);
+            if (q_hi < n) *reinterpret_cast<float4*>(o_hi) = make_float4(o[0][2] * i_hi, o[1][2] * i_hi, o[0][3] * i_hi, o[1][3] * i_hi);
+        } else {
+            if (q_lo < n) *reinterpret_cast<float2*>(o_lo) = make_float2(o[0][0] * i_lo, o[0][1] * i_lo);
+            if (q_hi < n) *reinterpret_cast<float2*>(o_hi) = make_float2(o[0][2] * i_hi, o[0][3] * i_hi);
         }
         if (t == 0) {
             if (q_lo < n) lse[(size_t)(r0 + q_lo) * H + h] = (m_lo + log2f(l_lo)) * LN2;
