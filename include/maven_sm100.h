@@ -45,6 +45,7 @@ extern "C" {
 const char* mvn_last_error(void);
 int         mvn_abi_version(void);
 int         mvn_num_sms(void);   /* SM count of the current device (148 on B200) */
+int         mvn_num_slabs(void); /* row slabs every partial-sum workspace is split into (sizes the *_workspace_bytes results) */
 long long   mvn_launch_count(void);   /* kernels this process has enqueued through the library */
 /* Per-kernel-class device timing for the roofline leg of bench.py: while a class bit is set, every launch of
  * that class is bracketed by CUDA events on its own stream; mvn_prof_read sums and clears them.

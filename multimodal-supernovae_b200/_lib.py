@@ -30,6 +30,7 @@ _SIGS = {
     "mvn_last_error": (c_char_p, []),
     "mvn_abi_version": (c_int, []),
     "mvn_num_sms": (c_int, []),
+    "mvn_num_slabs": (c_int, []),
     "mvn_launch_count": (ctypes.c_longlong, []),
     "mvn_prof_enable": (None, [ctypes.c_uint]),
     "mvn_prof_read": (c_int, [c_int, POINTER(c_double), POINTER(ctypes.c_longlong)]),

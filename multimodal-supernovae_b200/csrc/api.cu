@@ -77,3 +77,4 @@ extern "C" long long mvn_launch_count(void) { return mvn::g_launches; }
 extern "C" const char* mvn_last_error(void) { return mvn::g_err; }
 extern "C" int mvn_abi_version(void) { return 1; }
 extern "C" int mvn_num_sms(void) { return mvn::num_sms(); }
+extern "C" int mvn_num_slabs(void) { return mvn::kSlabs; }

@@ -69,7 +69,7 @@ struct ProfScope {
 };
 
 // number of row-slabs every weight-gradient style reduction is split into (partials are [kSlabs][...])
-constexpr int kSlabs = 128;
+constexpr int kSlabs = 148;      // one slab per B200 SM: every slab-partitioned kernel (weight gradients, LayerNorm backward, statistics) fills the GPU
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -377,7 +377,7 @@ class LinearResLNFn(torch.autograd.Function):
         dz = torch.empty_like(dy)
         dg = torch.empty(N, dtype=torch.float32, device=dy.device)
         dbt = torch.empty_like(dg)
-        wsb = max(L.mvn_linear_bwd_weight_workspace_bytes(M, N, K), 128 * 2 * N * 4)
+        wsb = max(L.mvn_linear_bwd_weight_workspace_bytes(M, N, K), L.mvn_num_slabs() * 2 * N * 4)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dy.device)
         check(L.mvn_layernorm_bwd(_p(dy), _p(xhat), _p(rstd), _p(gamma), _p(dz), _p(dg), _p(dbt), None, M, N, _p(ws), wsb, _stream()), "layernorm_bwd")
         dx = torch.empty(M, K, dtype=torch.float32, device=dy.device)
@@ -421,7 +421,7 @@ class FFNResLNFn(torch.autograd.Function):
         dev = dy.device
         dy = _req(dy, "grad_output").reshape(M, E)
         f32 = dict(dtype=torch.float32, device=dev)
-        wsb = max(L.mvn_linear_bwd_weight_workspace_bytes(M, F, E), 128 * 2 * E * 4)
+        wsb = max(L.mvn_linear_bwd_weight_workspace_bytes(M, F, E), L.mvn_num_slabs() * 2 * E * 4)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         dz = torch.empty(M, E, **f32); dg = torch.empty(E, **f32); dbt = torch.empty(E, **f32)
         check(L.mvn_layernorm_bwd(_p(dy), _p(xhat), _p(rstd), _p(gamma), _p(dz), _p(dg), _p(dbt), None, M, E, _p(ws), wsb, _stream()), "layernorm_bwd")
