@@ -1,0 +1,43 @@
+import ctypes, math, os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from maven_b200 import _lib
+L = _lib.lib()
+P = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+S = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+dev = torch.device("cuda:0")
+for (M, N, K, mode) in [(60001, 64, 256, "addend")] * 10 + [(60001, 64, 256, "relu_mask")] * 10:
+    torch.manual_seed(N * K)
+    dy = torch.randn(M, N); w = torch.randn(N, K) / math.sqrt(N); add = torch.randn(M, K); src = torch.randn(M, K)
+    ref = dy.double() @ w.double()
+    if mode == "addend": ref = ref + add.double()
+    if mode == "relu_mask": ref = ref * (src.double() > 0)
+    dyg, wg, addg, srcg = (v.to(dev) for v in (dy, w, add, src))
+    dx = torch.full((M, K), float("nan"), device=dev)
+    rc = L.mvn_linear_bwd_input(P(dyg), P(wg), P(dx), P(addg) if mode == "addend" else None, P(srcg) if mode == "relu_mask" else None,
+                                1 if mode == "relu_mask" else 0, None, M, N, K, 1, S())
+    torch.cuda.synchronize()
+    d = (dx.cpu().double() - ref).abs()
+    bad = d > 0.05
+    print(M, N, K, mode, "rc", rc, "bad frac", bad.float().mean().item(), "nan", torch.isnan(dx).sum().item())
+    if bad.any():
+        tiles = bad.view(-1)[: (M // 128) * 128 * K].view(M // 128, 128, K // 32, 32).any(dim=3).any(dim=1)   # [tile, chunk]
+        bt = tiles.any(dim=1).nonzero().flatten()
+        print("  bad tiles:", bt[:24].tolist(), "... count", len(bt), " CTA-seq of bad tiles (tile//148):", sorted(set((bt // 148).tolist())))
+        print("  bad chunks in first bad tiles:", [tiles[t].nonzero().flatten().tolist() for t in bt[:6]])
+        t0 = int(bt[0]); r = bad[t0 * 128:(t0 + 1) * 128].any(dim=1).nonzero().flatten()
+        print("  bad rows in tile", t0, ":", r.tolist(), "count", len(r))
+        if mode == "addend":
+            ch = int(tiles[t0].nonzero().flatten()[0])
+            base = (dy.double() @ w.double())
+            for row in r[:6].tolist():
+                gr = t0 * 128 + row
+                used = dx[gr, ch * 32:(ch + 1) * 32].cpu().double() - base[gr, ch * 32:(ch + 1) * 32]
+                # which (tile, chunk) of `add` matches what the kernel added?
+                best = None
+                for tt in (t0, t0 + 148, t0 + 296):
+                    if (tt + 1) * 128 > M: continue
+                    for cc in range(K // 32):
+                        e = (add[tt * 128 + row, cc * 32:(cc + 1) * 32].double() - used).abs().max().item()
+                        if best is None or e < best[0]: best = (e, tt, cc)
+                print("    row", row, "chunk", ch, "-> kernel added add[tile %d, chunk %d] (err %.2e)" % (best[1], best[2], best[0]))

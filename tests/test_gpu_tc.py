@@ -31,7 +31,7 @@ def S():
 
 
 SHAPES = [(5000, 192, 64), (777, 64, 64), (4097, 256, 64), (3000, 64, 256), (2500, 96, 32), (1300, 32, 32), (2049, 128, 32),
-          (1500, 32, 128), (128, 64, 192), (20000, 32, 96)]
+          (1500, 32, 128), (128, 64, 192), (20000, 32, 96), (60001, 192, 64), (60000, 256, 64), (77777, 32, 32)]
 
 
 @pytest.mark.parametrize("M,N,K", SHAPES)
@@ -64,7 +64,8 @@ def test_tc_linear_fwd_device_row_count(L):
     assert (y[n:] == 7.0).all()
 
 
-@pytest.mark.parametrize("M,N,K", [(3333, 64, 64), (1000, 32, 32), (2000, 64, 256), (900, 32, 128)])
+# the (60000+, ...) cases give every persistent CTA 3+ tiles: both epilogue groups run and every ring wraps around
+@pytest.mark.parametrize("M,N,K", [(3333, 64, 64), (1000, 32, 32), (2000, 64, 256), (900, 32, 128), (60001, 64, 64), (70000, 32, 128), (60000, 64, 256)])
 def test_tc_linear_res_ln(L, M, N, K):
     torch.manual_seed(N + K)
     x = torch.randn(M, K); w = torch.randn(N, K) / math.sqrt(K); b = torch.randn(N); r = torch.randn(M, N)
@@ -82,7 +83,8 @@ def test_tc_linear_res_ln(L, M, N, K):
     assert relerr(rstd, 1 / torch.sqrt(var + 1e-5).flatten()) < TOL_TC
 
 
-@pytest.mark.parametrize("M,N,K", [(3000, 192, 64), (2222, 64, 256), (1500, 256, 64), (4000, 96, 32), (1000, 128, 32), (1000, 32, 128)])
+@pytest.mark.parametrize("M,N,K", [(3000, 192, 64), (2222, 64, 256), (1500, 256, 64), (4000, 96, 32), (1000, 128, 32), (1000, 32, 128),
+                                   (60001, 64, 256), (61000, 256, 64), (59999, 192, 64), (80000, 32, 128)])
 @pytest.mark.parametrize("mode", ["plain", "addend", "relu_mask"])
 def test_tc_linear_bwd_input(L, M, N, K, mode):
     """dX[M,K] = dY[M,N] W[N,K] (+addend) (* relu mask)."""
