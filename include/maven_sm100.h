@@ -241,6 +241,22 @@ int mvn_convmixer_bwd_stage(const mvn_conv_cfg* cfg, int stage, const float* par
                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * N1 (next row): NoisyDataLoader.__iter__ on the device.  src/dataloader.py:88-287.
+ *   mvn_augment_seq:    out = x + noise * err * level        (:125 "mag + randn_like(mag) * magerr * noise_level_mag", same for spectra)
+ *   mvn_image_noise_range: range = max_noise_intensity * std(imgs) (unbiased std over the whole batch, :93)
+ *   mvn_augment_images: out[b] = rot90^{rot_k[b]}( img[b] + (2*noise_u - 1) * range )   (:96-112; RandomRotation([a,a]) with
+ *                       a = 90*k is exactly the counter-clockwise index permutation torch.rot90(img, k, (1,2)))
+ * `noise` / `noise_u` NULL: draw N(0,1) / U[0,1) in-kernel from `seed`; given: the result is bit-identical to the torch
+ * expression.  `img` is fp32 [B,C,H,W] (is_u8 = 0) or the raw 8-bit pixels, planar [B,C,H,W] (is_u8 = 1) or in the decoder's
+ * [B,H,W,C] order (is_u8 = 2; mvn_augment_images only), converted as float(v)/255 like load_images (:326-331). */
+int mvn_augment_seq(const float* x, const float* err, const float* noise, float level, int64_t n, uint64_t seed, float* out, void* stream);
+size_t mvn_image_noise_range_workspace_bytes(void);
+int mvn_image_noise_range(const void* img, int is_u8, int64_t n, float max_noise_intensity, float* range_out, void* workspace,
+                          size_t workspace_bytes, void* stream);
+int mvn_augment_images(const void* img, int is_u8, const float* noise_u, const int32_t* rot_k, const float* range_dev, uint64_t seed,
+                       int B, int C, int H, int W, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * A12 heads: weighted cross-entropy (src/models_multimodal.py:335-349) and MSE (:326).
  * labels are int64 (torch .long()).  loss = sum_i w[y_i] nll_i / sum_i w[y_i]. */
 int mvn_weighted_ce_fwd(const float* logits, const int64_t* labels, const float* class_w, int B, int C,

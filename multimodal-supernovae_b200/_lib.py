@@ -56,6 +56,10 @@ _SIGS = {
     "mvn_l2norm_bwd": (c_int, [P, P, P, P, c_int, c_int, P]),
     "mvn_dropout_scale": (c_int, [c_uint64, c_int, c_float, c_int, c_int, P, P]),
     "mvn_dropout_apply": (c_int, [P, P, c_int, c_int, c_uint64, c_int, c_float, P]),
+    "mvn_augment_seq": (c_int, [P, P, P, c_float, c_int64, c_uint64, P, P]),
+    "mvn_image_noise_range_workspace_bytes": (c_size_t, []),
+    "mvn_image_noise_range": (c_int, [P, c_int, c_int64, c_float, P, P, c_size_t, P]),
+    "mvn_augment_images": (c_int, [P, c_int, P, P, P, c_uint64, c_int, c_int, c_int, c_int, P, P]),
     "mvn_seq_param_count": (c_size_t, [POINTER(SeqCfg)]),
     "mvn_seq_workspace_bytes": (c_size_t, [POINTER(SeqCfg)]),
     "mvn_seq_encoder_fwd": (c_int, [POINTER(SeqCfg), P, P, P, P, P, P, P, c_size_t, P]),

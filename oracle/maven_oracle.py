@@ -347,3 +347,20 @@ def retrieval_ranks(e1: Tensor, e2: Tensor) -> Tensor:
     source e2_j in the descending argsort over e1 (ties aside)."""
     sim = F.normalize(e1, dim=-1) @ F.normalize(e2, dim=-1).T
     return (sim > sim.diag()[None, :]).sum(dim=0)
+
+
+# --------------------------------------------------------------------------------------
+# N1  NoisyDataLoader.__iter__ on GIVEN random tensors             src/dataloader.py:88-287
+# (the reference draws rand_like(images), randn_like(mag), randn_like(spec), randint(0,4) from
+# torch's global generator; tests/golden/make_golden_noisy.py replays those draws against the
+# unmodified class, so parity is defined on the recovered tensors)
+# --------------------------------------------------------------------------------------
+def noisy_images(imgs: Tensor, img_u: Tensor, rot_k: Tensor, max_noise_intensity: float) -> Tensor:
+    noise_range = max_noise_intensity * torch.std(imgs)                       # :93
+    noisy = imgs + (2 * img_u - 1) * noise_range                              # :96-98
+    # RandomRotation([a, a]) with a = 90*k is exactly torch.rot90(img, k, (1, 2))  (:101-109; checked by make_golden_noisy.py)
+    return torch.stack([torch.rot90(noisy[i], int(rot_k[i]), (1, 2)) for i in range(noisy.shape[0])])
+
+
+def noisy_seq(x: Tensor, err: Tensor, noise: Tensor, noise_level: float) -> Tensor:
+    return x + noise * err * noise_level                                      # :125, :136

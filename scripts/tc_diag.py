@@ -2,6 +2,8 @@ import ctypes, math, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from maven_b200 import _lib
+if os.environ.get('MVN_DIAG_LIB'):
+    _lib.LIB_PATH = os.environ['MVN_DIAG_LIB']
 L = _lib.lib()
 P = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
 S = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

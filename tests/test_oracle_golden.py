@@ -194,3 +194,15 @@ def test_convmixer_given_dropout_masks_match_torch_layers():
     got = O.convmixer(sd, "", img, depth=depth, kernel_size=k, patch_size=p, training=True, drop_scales=masks)
     assert relerr(got, ref) < 1e-12
     assert relerr(O.convmixer(sd, "", img, depth=depth, kernel_size=k, patch_size=p, training=True), ref) > 1e-3
+
+
+def test_noisy_loader_golden():
+    """N1: the oracle's augmentation == the reference NoisyDataLoader's outputs on the random tensors it consumed."""
+    g = load_golden("noisy_loader")
+    inten, lvl = float(g["max_noise_intensity"]), float(g["noise_level_mag"])
+    for case in ("img", "img_lc", "all"):
+        assert torch.equal(O.noisy_images(g["img"], g[f"{case}.img_u"], g[f"{case}.rot_k"], inten), g[f"{case}.out0"]), case
+    for case in ("lc", "img_lc", "lc_sp", "all"):
+        assert torch.equal(O.noisy_seq(g["mag"], g["magerr"], g[f"{case}.noise_mag"], lvl), g[f"{case}.out1"]), case
+    for case in ("lc_sp", "all"):
+        assert torch.equal(O.noisy_seq(g["spec"], g["specerr"], g[f"{case}.noise_spec"], lvl), g[f"{case}.out4"]), case
