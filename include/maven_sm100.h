@@ -275,7 +275,9 @@ int mvn_radam_step(float* param, const float* grad, float* exp_avg, float* exp_a
                    float bias_correction1, float sqrt_bias_correction2, float rect, void* stream);
 /* CUDA-graph form of the same update: the step count lives on the device (`step_dev`, incremented by this call) and the
  * step-dependent scalars (bias corrections, rectification) are computed from it on the device into `scalars_dev[3]`, so a
- * captured graph performs step t+1's update at its next replay.  All `n` elements share one step count. */
+ * captured graph performs step t+1's update at its next replay.  All `n` elements share one step count.  A step over several
+ * disjoint segments (parameters without a gradient are skipped, like torch does) passes `step_dev` for the first segment only
+ * and NULL for the rest, which then reuse the scalars. */
 int mvn_radam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                        float beta2, float eps, float weight_decay, uint32_t* step_dev, float* scalars_dev, void* stream);
 /* Registers a device-resident step counter (or NULL) that every dropout site mixes into its mask hash, in addition to the

@@ -162,10 +162,12 @@ extern "C" int mvn_radam_step(float* param, const float* grad, float* exp_avg, f
 
 extern "C" int mvn_radam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                                   float beta2, float eps, float weight_decay, uint32_t* step_dev, float* scalars_dev, void* stream) {
-    MVN_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && step_dev && scalars_dev, "radam_step_dev: bad arguments");
+    MVN_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && scalars_dev, "radam_step_dev: bad arguments");
     ProfScope prof(PROF_OPTIM, (cudaStream_t)stream);
-    radam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, scalars_dev, (double)beta1, (double)beta2);
-    MVN_LAUNCH_CHECK();
+    if (step_dev) {     // first segment of a step: advance the counter and refresh the scalars; later segments pass NULL and reuse them
+        radam_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, scalars_dev, (double)beta1, (double)beta2);
+        MVN_LAUNCH_CHECK();
+    }
     const long long blocks = (n + 255) / 256;
     radam_dev_kernel<<<(int)(blocks < 2368 ? blocks : 2368), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                                                            weight_decay, scalars_dev);

@@ -46,8 +46,8 @@ class FusedRAdam(torch.optim.Optimizer):
         flat = g.ensure()
         self._ensure_state(g, flat)
         start = max(self._steps) if self._steps else 0
-        if self._steps and min(self._steps) != start:
-            raise RuntimeError("FusedRAdam: device-side stepping needs every parameter at the same step count")
+        if any(s_ not in (0, start) for s_ in self._steps):       # 0: parameters that never receive a gradient (e.g. logit_scale of a classifier)
+            raise RuntimeError("FusedRAdam: device-side stepping needs every stepped parameter at the same step count")
         self._step_dev = torch.full((1,), start, dtype=torch.int32, device=flat.device)
         self._scal_dev = torch.zeros(4, dtype=torch.float32, device=flat.device)
         ops.set_step_counter(self._step_dev)
@@ -56,14 +56,16 @@ class FusedRAdam(torch.optim.Optimizer):
         """Back to host-side stepping (eager mode); the host mirror of the step count carries on from the device's."""
         if getattr(self, "_step_dev", None) is not None:
             n = int(self._step_dev.item())
-            self._steps = [n] * len(self._steps)
+            stepped = getattr(self, "_stepped", None)
+            self._steps = [n if (stepped is None or stepped[k]) else s for k, s in enumerate(self._steps)]
             if ops._STEP_COUNTER is self._step_dev:
                 ops.set_step_counter(None)
             self._step_dev = self._scal_dev = None
 
     def note_graph_replay(self):
         if self._steps is not None:
-            self._steps = [s + 1 for s in self._steps]
+            stepped = getattr(self, "_stepped", None)
+            self._steps = [s + 1 if (stepped is None or stepped[k]) else s for k, s in enumerate(self._steps)]
 
     def _ensure_state(self, g: ops.FlatParams, flat: torch.Tensor):
         if self._m is None or self._m.numel() != g.total or self._m.device != flat.device:
@@ -99,14 +101,19 @@ class FusedRAdam(torch.optim.Optimizer):
         lr, (b1, b2), eps, wd = grp["lr"], grp["betas"], grp["eps"], grp["weight_decay"]
         stream = ops._stream()
         if getattr(self, "_step_dev", None) is not None:
-            if len(runs) != 1 or runs[0][0] != 0 or runs[0][1] != g.total:
-                raise RuntimeError("FusedRAdam: device-side stepping needs a gradient for every parameter at every step")
-            for k in range(len(self._steps)):
-                self._steps[k] -= 1                  # the device counter is the truth; note_graph_replay() advances the mirror
-            check(L.mvn_radam_step_dev(ctypes.c_void_p(flat.data_ptr()), ctypes.c_void_p(gbuf.data_ptr()), ctypes.c_void_p(self._m.data_ptr()),
-                                       ctypes.c_void_p(self._v.data_ptr()), g.total, lr, b1, b2, eps, wd,
-                                       ctypes.c_void_p(self._step_dev.data_ptr()), ctypes.c_void_p(self._scal_dev.data_ptr()), stream), "radam_step_dev")
-            ops._count(2)
+            if len({r[2] for r in runs}) > 1:
+                raise RuntimeError("FusedRAdam: device-side stepping needs every stepped parameter at the same step count")
+            self._stepped = [False] * len(self._steps)
+            for k, p in enumerate(g.params):
+                if p.grad is not None and id(p) in in_group:
+                    self._stepped[k] = True
+                    self._steps[k] -= 1              # the device counter is the truth; note_graph_replay() advances the mirror
+            for i, (o0, o1, _) in enumerate(runs):   # parameters without a gradient are skipped, like torch.optim.RAdam does
+                check(L.mvn_radam_step_dev(ctypes.c_void_p(flat.data_ptr() + 4 * o0), ctypes.c_void_p(gbuf.data_ptr() + 4 * o0),
+                                           ctypes.c_void_p(self._m.data_ptr() + 4 * o0), ctypes.c_void_p(self._v.data_ptr() + 4 * o0), o1 - o0,
+                                           lr, b1, b2, eps, wd, ctypes.c_void_p(self._step_dev.data_ptr()) if i == 0 else None,
+                                           ctypes.c_void_p(self._scal_dev.data_ptr()), stream), "radam_step_dev")
+                ops._count(2 if i == 0 else 1)
             if not torch.cuda.is_current_stream_capturing():
                 self.note_graph_replay()             # an eager call in device-step mode really executed a step
             return loss

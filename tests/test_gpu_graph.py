@@ -30,7 +30,7 @@ def _make(wname, dropout, B=48):
     return model, opt, batches
 
 
-@pytest.mark.parametrize("wname", ["c4", "c5"])
+@pytest.mark.parametrize("wname", ["c4", "c5", "c2"])      # c2: classifier, logit_scale / logit_bias get no gradient
 def test_graphed_steps_match_eager_trajectory(wname):
     from maven_b200 import ops
     from maven_b200.graph import GraphedTrainStep
