@@ -6,8 +6,8 @@
 // MMA while its softmax costs ~6 instructions per score; the kernel is bound by the exp/scale pipeline, and a
 // TMEM round trip per score tile (tcgen05.ld / st) would add traffic without removing any of that work.
 //
-// One CTA per (sequence, head), 4 warps.  Forward: a warp owns 16 query rows, streams the keys in blocks of 64 with
-// an online softmax.  Backward: phase 1 (dQ, warp owns 16 queries, streams keys) and phase 2 (dK/dV, warp owns 16
+// One CTA per (sequence, head), 4 warps.  Forward: a warp owns 16 query rows, streams the keys in guard-free blocks of
+// 64 / 32 (zero-padded) with an online softmax.  Backward: phase 1 (dQ, warp owns 16 queries, streams keys) and phase 2 (dK/dV, warp owns 16
 // keys, streams queries) recompute probabilities from the saved log-sum-exp; no atomics, deterministic.
 // The probability / dS accumulator fragments are fed back as the A operand of the next MMA without any shuffle by
 // relabelling the contraction index (k = t <-> column 2t, k = t+4 <-> column 2t+1) consistently on the B side.
@@ -62,21 +62,6 @@ __device__ __forceinline__ void load_slice(float* dst, const float* __restrict__
         *reinterpret_cast<float4*>(dst + j * LD + d) = make_float4(tf32r(v.x * mul), tf32r(v.y * mul), tf32r(v.z * mul), tf32r(v.w * mul));
     }
 }
-// A-operand fragments (16 rows starting at row0, HD columns) straight from global memory; rows >= limit read as 0.
-template <int HD>
-__device__ __forceinline__ void load_afrag(float (*a)[4], const float* __restrict__ src, size_t ld, int col, int row0, int limit, float mul, int g, int t) {
-#pragma unroll
-    for (int ks = 0; ks < HD / 8; ++ks) {
-        const int r_lo = row0 + g, r_hi = row0 + g + 8;
-        const float* p_lo = src + (size_t)r_lo * ld + col + ks * 8 + t;
-        const float* p_hi = src + (size_t)r_hi * ld + col + ks * 8 + t;
-        a[ks][0] = r_lo < limit ? tf32r(__ldg(p_lo) * mul) : 0.f;
-        a[ks][1] = r_hi < limit ? tf32r(__ldg(p_hi) * mul) : 0.f;
-        a[ks][2] = r_lo < limit ? tf32r(__ldg(p_lo + 4) * mul) : 0.f;
-        a[ks][3] = r_hi < limit ? tf32r(__ldg(p_hi + 4) * mul) : 0.f;
-    }
-}
-
 // ---- operand relabelling -------------------------------------------------------------------------------------------
 // An MMA's contraction slots and output columns can be assigned to head dimensions in any order as long as both operands
 // (resp. the consumer of the accumulator) agree.  Two assignments make every shared-memory fragment load a vector load:
@@ -120,6 +105,18 @@ __device__ __forceinline__ void load_afrag_pi(float (*a)[4], const float* __rest
     for (int ks = 0; ks < HD / 8; ++ks) {
         a[ks][0] = tf32r(lo[2 * ks] * mul); a[ks][1] = tf32r(hi[2 * ks] * mul);
         a[ks][2] = tf32r(lo[2 * ks + 1] * mul); a[ks][3] = tf32r(hi[2 * ks + 1] * mul);
+    }
+}
+// accumulator tiles whose output columns are under sigma: lane t holds dims [2t*KS, 2t*KS + 2*KS) of rows g (c0,c1) and g+8 (c2,c3)
+template <int HD>
+__device__ __forceinline__ void store_sigma(float* __restrict__ p_lo, float* __restrict__ p_hi, const float (*acc)[4], float mul, bool w_lo, bool w_hi, int t) {
+    constexpr int KS = HD / 8;
+    if constexpr (KS == 2) {
+        if (w_lo) *reinterpret_cast<float4*>(p_lo + 4 * t) = make_float4(acc[0][0] * mul, acc[1][0] * mul, acc[0][1] * mul, acc[1][1] * mul);
+        if (w_hi) *reinterpret_cast<float4*>(p_hi + 4 * t) = make_float4(acc[0][2] * mul, acc[1][2] * mul, acc[0][3] * mul, acc[1][3] * mul);
+    } else {
+        if (w_lo) *reinterpret_cast<float2*>(p_lo + 2 * t) = make_float2(acc[0][0] * mul, acc[0][1] * mul);
+        if (w_hi) *reinterpret_cast<float2*>(p_hi + 2 * t) = make_float2(acc[0][2] * mul, acc[0][3] * mul);
     }
 }
 // like load_slice, but rows up to the next multiple of 32 are zero-filled (branch-free 32-key blocks)
@@ -273,9 +270,9 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
         const int q0 = rd * 64 + warp * 16;
         const bool active = q0 < n;
         const int q_lo = q0 + g, q_hi = q0 + g + 8;
-        float qa[HD / 8][4], ga[HD / 8][4];
-        load_afrag<HD>(qa, base, ld, h * HD, q0, n, scale * LOG2E, g, t);
-        load_afrag<HD>(ga, gbase, (size_t)E, 0, q0, n, 1.0f, g, t);
+        float qa[HD / 8][4], ga[HD / 8][4];                       // contraction slots relabelled by pi (see the forward)
+        load_afrag_pi<HD>(qa, base, ld, h * HD, q0, n, scale * LOG2E, g, t);
+        load_afrag_pi<HD>(ga, gbase, (size_t)E, 0, q0, n, 1.0f, g, t);
         // D for rows g / g+8: each lane of the quad takes HD/4 of the dims
         float D_lo = 0.f, D_hi = 0.f, L_lo = INFINITY, L_hi = INFINITY;
 #pragma unroll
@@ -304,27 +301,28 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
             for (int j = 0; j < ntile; ++j) {
                 const int key0 = j * 8;
                 float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+                float kf[HD / 4], vf[HD / 4];
+                lds_vec<HD>(kf, As + (key0 + g) * LD + t * (HD / 4));
+                lds_vec<HD>(vf, Bs + (key0 + g) * LD + t * (HD / 4));
 #pragma unroll
                 for (int ks = 0; ks < HD / 8; ++ks) {
-                    mma_tf32(s, qa[ks], As[(key0 + g) * LD + ks * 8 + t], As[(key0 + g) * LD + ks * 8 + t + 4]);
-                    mma_tf32(dp, ga[ks], Bs[(key0 + g) * LD + ks * 8 + t], Bs[(key0 + g) * LD + ks * 8 + t + 4]);
+                    mma_tf32(s, qa[ks], kf[2 * ks], kf[2 * ks + 1]);
+                    mma_tf32(dp, ga[ks], vf[2 * ks], vf[2 * ks + 1]);
                 }
                 // no key mask needed: rows of K past the sequence end are zero-filled in shared memory, so whatever (finite) dS
                 // they get multiplies a zero row in the dQ MMA below
                 const float p0 = ex2(s[0] - L_lo), p1 = ex2(s[1] - L_lo);
                 const float p2 = ex2(s[2] - L_hi), p3 = ex2(s[3] - L_hi);
                 const float da[4] = {tf32r(p0 * (dp[0] - D_lo)), tf32r(p2 * (dp[2] - D_hi)), tf32r(p1 * (dp[1] - D_lo)), tf32r(p3 * (dp[3] - D_hi))};
+                float k0[HD / 8], k1[HD / 8];                      // output columns relabelled by sigma
+                lds_half<HD>(k0, As + (key0 + 2 * t) * LD + g * (HD / 8));
+                lds_half<HD>(k1, As + (key0 + 2 * t + 1) * LD + g * (HD / 8));
 #pragma unroll
-                for (int nt = 0; nt < HD / 8; ++nt)
-                    mma_tf32(dq[nt], da, As[(key0 + 2 * t) * LD + nt * 8 + g], As[(key0 + 2 * t + 1) * LD + nt * 8 + g]);
+                for (int nt = 0; nt < HD / 8; ++nt) mma_tf32(dq[nt], da, k0[nt], k1[nt]);
             }
         }
         if (!active) continue;
-#pragma unroll
-        for (int nt = 0; nt < HD / 8; ++nt) {
-            if (q_lo < n) *reinterpret_cast<float2*>(dqkv + (size_t)(r0 + q_lo) * ld + h * HD + nt * 8 + 2 * t) = make_float2(dq[nt][0] * scale, dq[nt][1] * scale);
-            if (q_hi < n) *reinterpret_cast<float2*>(dqkv + (size_t)(r0 + q_hi) * ld + h * HD + nt * 8 + 2 * t) = make_float2(dq[nt][2] * scale, dq[nt][3] * scale);
-        }
+        store_sigma<HD>(dqkv + (size_t)(r0 + q_lo) * ld + h * HD, dqkv + (size_t)(r0 + q_hi) * ld + h * HD, dq, scale, q_lo < n, q_hi < n, t);
     }
 
     // ---- phase 2: dV_j = sum_i P_ij dO_i ; dK_j = scale * sum_i dS_ij Q_i ; warp owns 16 keys -----------------
@@ -332,8 +330,8 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
         const int k0 = rd * 64 + warp * 16;
         const bool active = k0 < n;
         float ka[HD / 8][4], va[HD / 8][4];
-        load_afrag<HD>(ka, base, ld, E + h * HD, k0, n, scale * LOG2E, g, t);
-        load_afrag<HD>(va, base, ld, 2 * E + h * HD, k0, n, 1.0f, g, t);
+        load_afrag_pi<HD>(ka, base, ld, E + h * HD, k0, n, scale * LOG2E, g, t);
+        load_afrag_pi<HD>(va, base, ld, 2 * E + h * HD, k0, n, 1.0f, g, t);
         float dk[HD / 8][4], dv[HD / 8][4];
 #pragma unroll
         for (int i = 0; i < HD / 8; ++i) { dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; }
@@ -365,37 +363,37 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
             for (int j = 0; j < ntile; ++j) {
                 const int qq = j * 8;
                 float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};      // transposed tiles: rows = keys, cols = queries
+                float qf[HD / 4], gf[HD / 4];
+                lds_vec<HD>(qf, As + (qq + g) * LD + t * (HD / 4));
+                lds_vec<HD>(gf, Bs + (qq + g) * LD + t * (HD / 4));
 #pragma unroll
                 for (int ks = 0; ks < HD / 8; ++ks) {
-                    mma_tf32(s, ka[ks], As[(qq + g) * LD + ks * 8 + t], As[(qq + g) * LD + ks * 8 + t + 4]);
-                    mma_tf32(dp, va[ks], Bs[(qq + g) * LD + ks * 8 + t], Bs[(qq + g) * LD + ks * 8 + t + 4]);
+                    mma_tf32(s, ka[ks], qf[2 * ks], qf[2 * ks + 1]);
+                    mma_tf32(dp, va[ks], gf[2 * ks], gf[2 * ks + 1]);
                 }
                 const int qc = qq + 2 * t;
                 const float L0 = lse_s[qc], L1 = lse_s[qc + 1], D0 = D_s[qc], D1 = D_s[qc + 1];
                 const float p0 = ex2(s[0] - L0), p1 = ex2(s[1] - L1), p2 = ex2(s[2] - L0), p3 = ex2(s[3] - L1);   // 0 on padding (L=+inf)
                 const float pa[4] = {tf32r(p0), tf32r(p2), tf32r(p1), tf32r(p3)};
                 const float da[4] = {tf32r(p0 * (dp[0] - D0)), tf32r(p2 * (dp[2] - D0)), tf32r(p1 * (dp[1] - D1)), tf32r(p3 * (dp[3] - D1))};
+                float g0[HD / 8], g1[HD / 8], q0v[HD / 8], q1v[HD / 8];
+                lds_half<HD>(g0, Bs + (qq + 2 * t) * LD + g * (HD / 8));
+                lds_half<HD>(g1, Bs + (qq + 2 * t + 1) * LD + g * (HD / 8));
+                lds_half<HD>(q0v, As + (qq + 2 * t) * LD + g * (HD / 8));
+                lds_half<HD>(q1v, As + (qq + 2 * t + 1) * LD + g * (HD / 8));
 #pragma unroll
                 for (int nt = 0; nt < HD / 8; ++nt) {
-                    mma_tf32(dv[nt], pa, Bs[(qq + 2 * t) * LD + nt * 8 + g], Bs[(qq + 2 * t + 1) * LD + nt * 8 + g]);
-                    mma_tf32(dk[nt], da, As[(qq + 2 * t) * LD + nt * 8 + g], As[(qq + 2 * t + 1) * LD + nt * 8 + g]);
+                    mma_tf32(dv[nt], pa, g0[nt], g1[nt]);
+                    mma_tf32(dk[nt], da, q0v[nt], q1v[nt]);
                 }
             }
         }
         if (!active) continue;
         const int k_lo = k0 + g, k_hi = k0 + g + 8;
-#pragma unroll
-        for (int nt = 0; nt < HD / 8; ++nt) {
-            const int col = h * HD + nt * 8 + 2 * t;
-            if (k_lo < n) {
-                *reinterpret_cast<float2*>(dqkv + (size_t)(r0 + k_lo) * ld + E + col) = make_float2(dk[nt][0] * scale, dk[nt][1] * scale);
-                *reinterpret_cast<float2*>(dqkv + (size_t)(r0 + k_lo) * ld + 2 * E + col) = make_float2(dv[nt][0], dv[nt][1]);
-            }
-            if (k_hi < n) {
-                *reinterpret_cast<float2*>(dqkv + (size_t)(r0 + k_hi) * ld + E + col) = make_float2(dk[nt][2] * scale, dk[nt][3] * scale);
-                *reinterpret_cast<float2*>(dqkv + (size_t)(r0 + k_hi) * ld + 2 * E + col) = make_float2(dv[nt][2], dv[nt][3]);
-            }
-        }
+        float* row_lo = dqkv + (size_t)(r0 + k_lo) * ld + h * HD;
+        float* row_hi = dqkv + (size_t)(r0 + k_hi) * ld + h * HD;
+        store_sigma<HD>(row_lo + E, row_hi + E, dk, scale, k_lo < n, k_hi < n, t);
+        store_sigma<HD>(row_lo + 2 * E, row_hi + 2 * E, dv, 1.0f, k_lo < n, k_hi < n, t);
     }
 }
 

@@ -8,7 +8,8 @@ L = _lib.lib()
 P = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
 S = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 dev = torch.device("cuda:0")
-for (M, N, K, mode) in [(60001, 64, 256, "addend")] * 10 + [(60001, 64, 256, "relu_mask")] * 10:
+REPS = int(os.environ.get("DIAG_REPS", "10"))
+for (M, N, K, mode) in [(60001, 64, 256, "addend")] * REPS + [(60001, 64, 256, "relu_mask")] * REPS:
     torch.manual_seed(N * K)
     dy = torch.randn(M, N); w = torch.randn(N, K) / math.sqrt(N); add = torch.randn(M, K); src = torch.randn(M, K)
     ref = dy.double() @ w.double()

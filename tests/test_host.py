@@ -123,3 +123,23 @@ def test_no_oracle_import_in_product():
         if f.endswith(".py") and f != "selfcheck.py":
             src = open(os.path.join(pkg, f)).read()
             assert "oracle" not in src.replace("# oracle", ""), f
+
+
+def test_graph_and_augment_refuse_cpu(built):
+    """The whole-step graph and the device-side augmentation are CUDA-only like everything else: CPU inputs raise."""
+    import torch
+    from maven_b200.augment import DeviceAugment, augment_images, augment_seq
+    from maven_b200.graph import GraphedTrainStep
+    from maven_b200.models_multimodal import LightCurveImageCLIP
+    m = LightCurveImageCLIP(combinations=["lightcurve"], nband=2, loss="softmax", regression=True,
+                            transformer_kwargs=dict(n_out=8, emb=16, heads=2, depth=1, time_norm=100.0, agg="mean"))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        GraphedTrainStep(m, None, [None] * 9)
+    with pytest.raises(RuntimeError, match="CUDA|CPU"):
+        augment_seq(torch.zeros(3), torch.zeros(3), 1.0)
+    with pytest.raises(RuntimeError, match="CUDA|CPU"):
+        augment_images(torch.zeros(1, 3, 4, 4), None)
+    with pytest.raises(ValueError, match="unsupported combination"):
+        DeviceAugment(["meta"], 0.1, 1.0)
+    with pytest.raises(ValueError, match="expected 3 tensors"):
+        DeviceAugment(["host_galaxy"], 0.1, 1.0)([torch.zeros(1)])
