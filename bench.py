@@ -435,9 +435,10 @@ def run_gpu(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        sps, sec = cpu_reference_steps(wl, args.ref_batch, 3, 1, threads)
+        n_cpu = 40                                              # ~10 s of host work at batch 64 on 16 cores (a bounded sample of the workload)
+        sps, sec = cpu_reference_steps(wl, args.ref_batch, n_cpu, 2, threads)
         cpu = {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
-               "sample": f"3 training steps (fwd+bwd+torch RAdam) at batch {args.ref_batch} of the same workload, oracle port, fp32, dense over padded T"}
+               "sample": f"{n_cpu} training steps (fwd+bwd+torch RAdam) at batch {args.ref_batch} of the same workload, oracle port, fp32, dense over padded T"}
     line = {
         "metric": "clip_train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
