@@ -58,9 +58,12 @@ def image_noise_range(imgs: torch.Tensor, max_noise_intensity: float) -> torch.T
 
 
 def augment_images(imgs: torch.Tensor, noise_range: Optional[torch.Tensor], rot_k: Optional[torch.Tensor] = None,
-                   noise_u: Optional[torch.Tensor] = None, seed: int = 0, layout: str = "bchw") -> torch.Tensor:
+                   noise_u: Optional[torch.Tensor] = None, seed: int = 0, layout: str = "bchw",
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """rot90^k(imgs + (2*rand - 1) * noise_range) -> fp32 (B,C,H,W)  (src/dataloader.py:93-112).  imgs: fp32 (B,C,H,W), uint8
-    (B,C,H,W) or, with layout='bhwc', the decoder's uint8 (B,H,W,C); rot_k int32 (B,) in 0..3 (counter-clockwise quarter turns)."""
+    (B,C,H,W) or, with layout='bhwc', the decoder's uint8 (B,H,W,C); rot_k int32 (B,) in 0..3 (counter-clockwise quarter turns).
+    noise_range None: no noise (a pure uint8 -> float32/255 conversion / rotation pass); out: write into an existing buffer, e.g.
+    the static image input of a GraphedTrainStep."""
     if not imgs.is_cuda:
         raise RuntimeError("maven_b200: images are on the CPU; CUDA only (no CPU fallback)")
     imgs = imgs.contiguous()
@@ -80,7 +83,10 @@ def augment_images(imgs: torch.Tensor, noise_range: Optional[torch.Tensor], rot_
         rot_k = rot_k.to(device=imgs.device, dtype=torch.int32).contiguous()
     if noise_u is not None:
         noise_u = ops._req(noise_u, "noise_u")
-    out = torch.empty(B, C, H, W, dtype=torch.float32, device=imgs.device)
+    if out is None:
+        out = torch.empty(B, C, H, W, dtype=torch.float32, device=imgs.device)
+    elif tuple(out.shape) != (B, C, H, W) or out.dtype != torch.float32 or not out.is_cuda or not out.is_contiguous():
+        raise ValueError(f"augment_images: `out` must be a contiguous float32 CUDA tensor of shape {(B, C, H, W)}")
     check(lib().mvn_augment_images(_p(imgs), mode, _p(noise_u), _p(rot_k), _p(noise_range), int(seed) & 0xFFFFFFFFFFFFFFFF, B, C, H, W, _p(out),
                                    ops._stream()), "augment_images")
     ops._count(1)

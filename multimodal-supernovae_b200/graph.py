@@ -8,6 +8,10 @@ What changes from step to step inside a graph (whose kernel arguments are frozen
   * dropout masks  -> every dropout site mixes a device step counter into its hash (mvn_set_step_counter);
   * RAdam's bias corrections / rectification -> computed on the device from that counter (mvn_radam_step_dev).
 No host synchronisation happens inside `__call__`; the returned loss is a device tensor (call .item() to read it).
+Frozen at capture, like every kernel argument: the batch shapes, the learning rate / betas / weight decay of the optimizer
+(the reference trains with a constant-lr RAdam, src/models_multimodal.py:306-310) and which parameters receive gradients.
+`step.static[i]` are the device-resident inputs: a caller may fill one itself (e.g. maven_b200.augment.augment_images(...,
+out=step.static[0]) from an 8-bit upload) and pass that same tensor in the batch, which skips the copy for it.
 """
 from __future__ import annotations
 
