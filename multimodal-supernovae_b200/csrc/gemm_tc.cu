@@ -16,6 +16,7 @@
 //     load/store of C, the residual, xhat ... is a full 128-byte line (TMA loads in, TMA stores out).
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 
 #include "tc_common.cuh"
 
@@ -60,7 +61,12 @@ const CUtensorMap* get_tmap_2d(const float* base, int rows, int cols, int box_ro
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return nullptr; }
     if (g_maps.size() > 4096) {                    // pointers churn (caching allocator): keep the table bounded
-        for (auto& kv : g_maps) delete kv.second;
+        // Descriptors handed out before this call may still be dereferenced by the caller (a launch looks up to four of
+        // them before it copies them into the kernel parameters), so a purged generation is only freed at the NEXT purge.
+        static std::vector<CUtensorMap*> retired;
+        for (CUtensorMap* m : retired) delete m;
+        retired.clear();
+        for (auto& kv : g_maps) retired.push_back(kv.second);
         g_maps.clear();
     }
     CUtensorMap* m = new CUtensorMap;
