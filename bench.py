@@ -287,13 +287,6 @@ def run_gpu(args):
     pinned = [None if v is None else v.pin_memory() for v in host]
     resident = [None if v is None else v.to(dev) for v in host]
     h2d = sum(v.numel() * v.element_size() for v in pinned if v is not None)      # every tensor of the 9-tuple batch is copied per step
-    img_u8 = None
-    if wl.get("img") and args.graph:
-        # end-to-end leg of the image workloads: the host keeps the cut-outs as the 8-bit pixels they are; the device converts
-        # (maven_b200.augment, SURVEY §8f N1) straight into the graph's static image input -> 10.8 KB instead of 43.2 KB per sample
-        img_u8 = (host[0] * 255.0).round().to(torch.uint8).pin_memory()
-        assert torch.equal(img_u8.float() / 255.0, host[0])
-        h2d += img_u8.numel() - pinned[0].numel() * pinned[0].element_size()
     fl = flops_per_step(wl, host)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
 
@@ -341,11 +334,33 @@ def run_gpu(args):
     sync()
 
     # ---- the product's training step: the whole step as ONE CUDA graph (maven_b200.graph), replayed per batch -------------
-    graphed = None
+    graphed, graph_note = None, None
     if args.graph:
         from maven_b200.graph import GraphedTrainStep
-        graphed = GraphedTrainStep(model, opt, resident, group=dist.group.WORLD if world > 1 else None)
-
+        try:
+            graphed = GraphedTrainStep(model, opt, resident, group=dist.group.WORLD if world > 1 else None)
+        except Exception as e:                                 # same kernels, launched eagerly: never a different code path
+            graph_note = f"eager launches (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
+            print(f"[bench] rank {rank}: {graph_note}", file=sys.stderr, flush=True)
+            opt.disable_device_step()
+            opt.zero_grad(set_to_none=True)
+            torch.cuda.synchronize()
+        if world > 1:                                          # all ranks must take the same path (the collectives have to match)
+            ok = torch.tensor([1.0 if graphed is not None else 0.0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() == 0.0 and graphed is not None:
+                graphed = None
+                graph_note = "eager launches (graph capture failed on another rank)"
+                opt.disable_device_step()
+                opt.zero_grad(set_to_none=True)
+    img_u8 = None
+    if wl.get("img") and graphed is not None:
+        # end-to-end leg of the image workloads: the host keeps the cut-outs as the 8-bit pixels they are; the device converts
+        # (maven_b200.augment, SURVEY §8f N1) straight into the graph's static image input -> 10.8 KB instead of 43.2 KB per sample
+        img_u8 = (host[0] * 255.0).round().to(torch.uint8).pin_memory()
+        assert torch.equal(img_u8.float() / 255.0, host[0])
+        h2d += img_u8.numel() - pinned[0].numel() * pinned[0].element_size()
+    if graphed is not None:
         def run_step(batch):                                   # batch None: inputs already resident in the static buffers
             return graphed(batch)
         for _ in range(2):
@@ -461,7 +476,8 @@ def run_gpu(args):
                    "dropout": args.dropout, "precision": args.precision,
                    "streams": "one CUDA stream per modality encoder" if concurrent and len(wl["combinations"]) > 1 else "single stream",
                    "e2e_image_upload": "uint8 pixels, converted on the device (maven_b200.augment)" if img_u8 is not None else None,
-                   "launch": "whole step replayed as one CUDA graph (maven_b200.graph.GraphedTrainStep)" if graphed is not None else "eager launches",
+                   "launch": "whole step replayed as one CUDA graph (maven_b200.graph.GraphedTrainStep)" if graphed is not None
+                             else (graph_note or "eager launches"),
                    "l2": "256 MiB flush written between timed steps; per-step activation working set is GBs (>> 126 MB L2)",
                    "valid_token_fraction": {"lc": float(host[3].float().mean()), "sp": float(host[6].float().mean()) if host[6] is not None else None}},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
