@@ -143,3 +143,21 @@ def test_graph_and_augment_refuse_cpu(built):
         DeviceAugment(["meta"], 0.1, 1.0)
     with pytest.raises(ValueError, match="expected 3 tensors"):
         DeviceAugment(["host_galaxy"], 0.1, 1.0)([torch.zeros(1)])
+
+
+def test_device_augment_field_orders_match_reference_tuple_lengths():
+    """NoisyDataLoader asserts the dataset tuple length per combination set (src/dataloader.py:64-87): 3 = images only,
+    6 = one sequence modality, 7 = images + one sequence modality, 10 = light curve + spectra, 11 = all three."""
+    from maven_b200.augment import _FIELDS
+    want = {frozenset(["host_galaxy"]): 3, frozenset(["lightcurve"]): 6, frozenset(["spectral"]): 6,
+            frozenset(["host_galaxy", "lightcurve"]): 7, frozenset(["host_galaxy", "spectral"]): 7,
+            frozenset(["spectral", "lightcurve"]): 10, frozenset(["host_galaxy", "spectral", "lightcurve"]): 11}
+    assert {k: len(v) for k, v in _FIELDS.items()} == want
+    for fields in _FIELDS.values():
+        assert fields[-2:] == ("redshift", "classification")
+        if "mag" in fields:
+            i = fields.index("mag")
+            assert fields[i:i + 4] == ("mag", "time", "mask", "magerr")
+        if "spec" in fields:
+            i = fields.index("spec")
+            assert fields[i:i + 4] == ("spec", "freq", "maskspec", "specerr")
