@@ -314,12 +314,12 @@ def run_gpu(args):
     # ---- per-class device timing: K steps with every kernel class bracketed by CUDA events on the launching stream ---------
     # (kept out of the throughput region below: event records between launches would defeat the programmatic dependent
     # launches that overlap each tensor-core kernel's prologue with its predecessor's tail)
-    names = ["gemm", "wgrad", "attn_fwd", "attn_bwd", "row", "loss", "optim", "conv"]
+    names = ["gemm", "wgrad", "attn_fwd", "attn_bwd", "row", "loss", "optim", "conv", "fused_fwd", "fused_bwd"]
     # The class timing runs the modality encoders back to back on one stream (each kernel alone on the GPU, the roofline
     # definition); the throughput region below runs them on one stream each, as the product does by default.
     concurrent = model.concurrent_modalities
     model.concurrent_modalities = False
-    L.mvn_prof_enable(0xFF)
+    L.mvn_prof_enable(0x3FF)
     for _ in range(args.steps):
         flush.fill_(1)
         step(resident)
@@ -532,7 +532,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=64, help="samples per CPU reference step (bounded sample)")
     ap.add_argument("--dropout", type=float, default=0.00021844858312997214,
                     help="transformer dropout p (default: pretrain_config/maven_pretrain_config.yaml); the CPU reference arm uses 0")
-    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "fused"],
                     help="tf32: tcgen05/mma tensor-core tier (fp32 storage, fp32 accumulate; parity 1e-3); fp32: FFMA tier (parity 1e-5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="enqueue every kernel from Python instead of replaying the captured step")

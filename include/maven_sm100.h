@@ -17,7 +17,8 @@
  *     sequence b owns rows cu_seqlens[b] .. cu_seqlens[b+1]-1.  The live row count lives on the device
  *     (cu_seqlens[B]); `n_rows_dev` arguments point at it so no host read is needed (CUDA-graph safe).
  *   - `prec`: 0 = fp32 FFMA arithmetic (parity tier 1e-5); 1 = TF32 tensor-core contraction via tcgen05 with
- *     fp32 accumulate (parity tier 1e-3).  Storage is fp32 in both.
+ *     fp32 accumulate (parity tier 1e-3); 2 (whole-encoder calls) = tier 1 arithmetic with the fused block kernels that
+ *     keep per-layer intermediates on chip (per-op entry points treat 2 like 1).  Storage is fp32 in all tiers.
  *   - masks are the uint8 storage of torch.bool tensors (0/1).
  */
 #ifndef MAVEN_SM100_H
@@ -47,6 +48,11 @@ int         mvn_abi_version(void);
 int         mvn_num_sms(void);   /* SM count of the current device (148 on B200) */
 int         mvn_num_slabs(void); /* row slabs every partial-sum workspace is split into (sizes the *_workspace_bytes results) */
 long long   mvn_launch_count(void);   /* kernels this process has enqueued through the library */
+/* Which arithmetic tier the GEMM-class / attention launches of this process actually ran on: 0 FFMA kernels, 1 tcgen05
+ * (tc_gemm / tc_wgrad), 2 warp-MMA attention, 3 fused block kernels (ffn_fused / attn_fused).  A shape the tensor-core kernels
+ * do not cover runs on the FFMA kernel and is counted there, so a test can assert that nothing fell back. */
+long long   mvn_tier_count(int tier);
+void        mvn_tier_reset(void);
 /* Per-kernel-class device timing for the roofline leg of bench.py: while a class bit is set, every launch of
  * that class is bracketed by CUDA events on its own stream; mvn_prof_read sums and clears them.
  * classes: 0 GEMM (fwd + input-grad), 1 weight-grad GEMM, 2 attention fwd, 3 attention bwd, 4 row kernels
@@ -94,6 +100,25 @@ int mvn_linear_bwd_weight(const float* dY, const float* X, float* dW, float* db,
                           const int32_t* n_rows_dev, int M_cap, int N, int K, int accumulate,
                           void* workspace, size_t workspace_bytes, int prec, void* stream);
 size_t mvn_linear_bwd_weight_workspace_bytes(int M_cap, int N, int K);
+
+/* Feed-forward half of a TransformerBlock in ONE kernel (src/transformer_utils.py:101-105,113-115):
+ *   Y = dropout( LayerNorm( X + ff.2( relu( ff.0(X) ) ) ) * gamma + beta )        W1 [4E,E], W2 [E,4E]
+ * The hidden activation never reaches HBM.  Also writes xhat (normalised, pre-affine) and rstd[M] for the backward.
+ * TF32 warp-MMA contraction, fp32 accumulate.  E in {32, 64}, ff_mult == 4 (MVN_E_UNSUPPORTED otherwise).
+ * Dropout: keep-factor of mvn_dropout_scale(seed, site, p) applied to Y (xhat stays pre-dropout); p == 0 switches it off. */
+int mvn_ffn_fused_fwd(const float* X, const float* W1, const float* b1, const float* W2, const float* b2,
+                      const float* gamma, const float* beta, float* Y, float* xhat, float* rstd,
+                      const int32_t* n_rows_dev, int M_cap, int E, int ff_mult, float eps,
+                      float dropout_p, uint64_t seed, int site, void* stream);
+/* Its backward in ONE kernel (+ the fixed-order reduction of the per-SM partial sums): dropout and LayerNorm backward from
+ * (dY, xhat, rstd), h recomputed from X on chip, dX = dz + (dz W2 * relu') W1, and dW1, db1, dW2, db2, dgamma, dbeta. */
+size_t mvn_ffn_fused_bwd_workspace_bytes(int E, int ff_mult);
+int mvn_ffn_fused_bwd(const float* dY, const float* xhat, const float* rstd, const float* X,
+                      const float* W1, const float* b1, const float* W2, const float* gamma,
+                      float* dX, float* dW1, float* db1, float* dW2, float* db2, float* dgamma, float* dbeta,
+                      const int32_t* n_rows_dev, int M_cap, int E, int ff_mult,
+                      float dropout_p, uint64_t seed, int site,
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* dPre = dY * (H > 0): ReLU backward from the saved activation (MLP heads, src/models_multimodal.py:846-850). */
 int mvn_relu_bwd(const float* dY, const float* H, int64_t n, float* dPre, void* stream);
@@ -155,7 +180,7 @@ typedef struct {
     int32_t B, T, E, H, depth, nband, n_out, enc_dim;
     int32_t agg;          /* MVN_AGG_*                                             */
     int32_t normalize;    /* 1: L2-normalise the output rows (CLIP branch)          */
-    int32_t prec;         /* 0 fp32, 1 tf32 tensor cores                            */
+    int32_t prec;         /* 0 fp32, 1 tf32 tensor cores, 2 tf32 + fused block kernels */
     int32_t ff_mult;      /* 4 (Transformer default, src/transformer_utils.py:124)  */
     float   ln_eps;       /* 1e-5                                                   */
     float   dropout_p;    /* nn.Dropout p of Transformer/TransformerBlock (0 = off); counter-based in-kernel mask,

@@ -32,6 +32,8 @@ _SIGS = {
     "mvn_num_sms": (c_int, []),
     "mvn_num_slabs": (c_int, []),
     "mvn_launch_count": (ctypes.c_longlong, []),
+    "mvn_tier_count": (ctypes.c_longlong, [c_int]),
+    "mvn_tier_reset": (None, []),
     "mvn_prof_enable": (None, [ctypes.c_uint]),
     "mvn_prof_read": (c_int, [c_int, POINTER(c_double), POINTER(ctypes.c_longlong)]),
     "mvn_pack_plan": (c_int, [P, c_int, c_int, c_int, P, P, P, P]),
@@ -42,6 +44,9 @@ _SIGS = {
     "mvn_linear_bwd_input": (c_int, [P, P, P, P, P, c_int, P, c_int, c_int, c_int, c_int, P]),
     "mvn_linear_bwd_weight": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P, c_size_t, c_int, P]),
     "mvn_linear_bwd_weight_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "mvn_ffn_fused_fwd": (c_int, [P, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_float, c_float, c_uint64, c_int, P]),
+    "mvn_ffn_fused_bwd_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "mvn_ffn_fused_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_float, c_uint64, c_int, P, c_size_t, P]),
     "mvn_relu_bwd": (c_int, [P, P, c_int64, P, P]),
     "mvn_layernorm_bwd": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, P, c_size_t, P]),
     "mvn_attention_fwd": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_float, c_int, P]),

@@ -32,6 +32,8 @@ static const uint32_t* g_step_ctr = nullptr;
 const uint32_t* step_counter() { return g_step_ctr; }
 static long long g_launches = 0;
 void note_launch() { ++g_launches; }
+static long long g_tier[TIER_N] = {0, 0, 0, 0};
+void count_tier(int tier) { if (tier >= 0 && tier < TIER_N) ++g_tier[tier]; }
 
 static unsigned g_prof_mask = 0;
 struct ProfRec { cudaEvent_t a, b; };
@@ -73,6 +75,8 @@ extern "C" int mvn_prof_read(int cls, double* total_ms, long long* count) {
 }
 extern "C" void mvn_set_step_counter(const uint32_t* dev_counter) { mvn::g_step_ctr = dev_counter; }
 extern "C" long long mvn_launch_count(void) { return mvn::g_launches; }
+extern "C" long long mvn_tier_count(int tier) { return (tier >= 0 && tier < mvn::TIER_N) ? mvn::g_tier[tier] : -1; }
+extern "C" void mvn_tier_reset(void) { for (int i = 0; i < mvn::TIER_N; ++i) mvn::g_tier[i] = 0; }
 
 extern "C" const char* mvn_last_error(void) { return mvn::g_err; }
 extern "C" int mvn_abi_version(void) { return 1; }

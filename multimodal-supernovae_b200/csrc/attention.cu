@@ -254,10 +254,11 @@ extern "C" int mvn_attention_fwd(const float* qkv, const int32_t* cu_seqlens, co
     const int hd = E / H;
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope prof(PROF_ATTN_FWD, st);
-    if (prec == 1 && keyvalid == nullptr) {       // packed stream, every key live: tensor-core kernel
+    if (prec >= 1 && keyvalid == nullptr) {       // packed stream, every key live: tensor-core kernel
         const int r = launch_attention_fwd_tc(qkv, cu_seqlens, out, lse, B, E, H, scale, st);
-        if (r != MVN_E_UNSUPPORTED) return r;
+        if (r != MVN_E_UNSUPPORTED) { if (r == 0) count_tier(TIER_MMA); return r; }
     }
+    count_tier(TIER_FFMA);
     const int grid = B * H;
     switch (hd) {
         case 4: attn_fwd_kernel<4><<<grid, ATT_THREADS, 0, st>>>(qkv, cu_seqlens, keyvalid, out, lse, E, H, scale); break;
@@ -278,10 +279,11 @@ extern "C" int mvn_attention_bwd(const float* qkv, const int32_t* cu_seqlens, co
     const int hd = E / H;
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope prof(PROF_ATTN_BWD, st);
-    if (prec == 1 && keyvalid == nullptr) {
+    if (prec >= 1 && keyvalid == nullptr) {
         const int r = launch_attention_bwd_tc(qkv, cu_seqlens, out, lse, dout, dqkv, B, E, H, scale, st);
-        if (r != MVN_E_UNSUPPORTED) return r;
+        if (r != MVN_E_UNSUPPORTED) { if (r == 0) count_tier(TIER_MMA); return r; }
     }
+    count_tier(TIER_FFMA);
     const int grid = B * H;
     switch (hd) {
         case 4: attn_bwd_kernel<4><<<grid, ATT_THREADS, 0, st>>>(qkv, cu_seqlens, keyvalid, out, lse, dout, dqkv, E, H, scale); break;

@@ -61,7 +61,10 @@ int num_sms();
 void note_launch();
 
 // per-kernel-class device timing (bench.py's roofline leg): CUDA events on the launching stream
-enum ProfClass { PROF_GEMM = 0, PROF_WGRAD = 1, PROF_ATTN_FWD = 2, PROF_ATTN_BWD = 3, PROF_ROW = 4, PROF_LOSS = 5, PROF_OPTIM = 6, PROF_CONV = 7, PROF_NCLASS = 8 };
+enum ProfClass { PROF_GEMM = 0, PROF_WGRAD = 1, PROF_ATTN_FWD = 2, PROF_ATTN_BWD = 3, PROF_ROW = 4, PROF_LOSS = 5, PROF_OPTIM = 6, PROF_CONV = 7, PROF_FUSED_FWD = 8, PROF_FUSED_BWD = 9, PROF_NCLASS = 10 };
+// which arithmetic tier a GEMM-class launch actually ran on (mvn_tier_count): tests assert that tensor-core shapes did not fall back
+enum Tier { TIER_FFMA = 0, TIER_TC = 1, TIER_MMA = 2, TIER_FUSED = 3, TIER_N = 4 };
+void count_tier(int tier);
 struct ProfScope {
     int cls; cudaStream_t st; cudaEvent_t stop; bool on;
     ProfScope(int cls_, cudaStream_t st_);
@@ -175,6 +178,15 @@ int launch_ln_bwd(const float* dY, const float* xhat, const float* rstd, const f
 int launch_embed_bwd_partials(const float* x, const int32_t* tok_src, const float* dout, const int32_t* n_rows_dev,
                               int M_cap, int T, int E, int nband, float* partial, size_t pstride, size_t off, cudaStream_t st,
                               const DropCfg& drop = DropCfg());
+// fused feed-forward half of a block (ffn_fused.cu); partial offsets are floats inside one slab
+bool ffn_fused_supported(int E, int ff_mult);
+int launch_ffn_fused_fwd(const float* X, const float* W1, const float* b1, const float* W2, const float* b2, const float* gamma,
+                         const float* beta, float* Y, float* xhat, float* rstd, const int32_t* n_rows_dev, int M_cap, int E, float eps,
+                         const DropCfg& drop, cudaStream_t st);
+int launch_ffn_fused_bwd(const float* dY, const float* xhat, const float* rstd, const float* X, const float* W1, const float* b1,
+                         const float* W2, const float* gamma, float* dX, const int32_t* n_rows_dev, int M_cap, int E, const DropCfg& drop,
+                         float* partial, size_t pstride, size_t o_w1, size_t o_b1, size_t o_w2, size_t o_b2, size_t o_g, size_t o_b,
+                         cudaStream_t st);
 int launch_embed_fwd(const float* x, const float* t, const int32_t* cu_seqlens, const int32_t* tok_src, const float* div_term,
                      const float* w, const float* b, const float* band_emb, int B, int T, int E, int nband, float* out,
                      cudaStream_t st, const DropCfg& drop);

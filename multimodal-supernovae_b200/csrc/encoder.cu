@@ -57,6 +57,7 @@ struct Workspace {
     char* layer_base; size_t layer_bytes;
     size_t bytes;
     size_t M, E, F, H;
+    bool fuse_ffn;          // prec 2: h / dh are never materialised
 
     LayerBuf layer(int l) const {
         char* p = layer_base + (size_t)l * layer_bytes;
@@ -64,7 +65,7 @@ struct Workspace {
         auto take = [&](size_t nfloat) { float* r = (float*)p; p += align_up(nfloat * sizeof(float), 256); return r; };
         b.qkv = take(M * 3 * E); b.att = take(M * E); b.lse = take(M * H);
         b.xhat1 = take(M * E); b.rstd1 = take(M); b.x1 = take(M * E);
-        b.h = take(M * F); b.xhat2 = take(M * E); b.rstd2 = take(M); b.x2 = take(M * E);
+        b.h = fuse_ffn ? nullptr : take(M * F); b.xhat2 = take(M * E); b.rstd2 = take(M); b.x2 = take(M * E);
         return b;
     }
 };
@@ -73,6 +74,7 @@ Workspace carve(const mvn_seq_cfg& c, void* base) {
     Workspace w;
     const size_t M = (size_t)c.B * c.T, E = c.E, F = (size_t)c.ff_mult * c.E, H = c.H, B = c.B;
     w.M = M; w.E = E; w.F = F; w.H = H;
+    w.fuse_ffn = c.prec == 2 && ffn_fused_supported(c.E, c.ff_mult);
     char* p = (char*)base;
     auto take = [&](size_t bytes) { char* r = p; p += align_up(bytes, 256); return r; };
     w.cu = (int32_t*)take((B + 1) * 4);
@@ -90,7 +92,7 @@ Workspace carve(const mvn_seq_cfg& c, void* base) {
     w.dA = (float*)take(M * E * 4);
     w.dz = (float*)take(M * E * 4);
     w.dqkv = (float*)take(M * 3 * E * 4);
-    w.dh = (float*)take(M * F * 4);
+    w.dh = w.fuse_ffn ? nullptr : (float*)take(M * F * 4);
     w.d_p2 = (float*)take(B * Dmax * 4);
     w.d_p1 = (float*)take(B * (size_t)c.n_out * 4);
     w.d_pooled = (float*)take(B * E * 4);
@@ -105,7 +107,7 @@ Workspace carve(const mvn_seq_cfg& c, void* base) {
     {
         size_t lb = 0;
         auto add = [&](size_t nfloat) { lb += align_up(nfloat * sizeof(float), 256); };
-        add(M * 3 * E); add(M * E); add(M * H); add(M * E); add(M); add(M * E); add(M * F); add(M * E); add(M); add(M * E);
+        add(M * 3 * E); add(M * E); add(M * H); add(M * E); add(M); add(M * E); if (!w.fuse_ffn) add(M * F); add(M * E); add(M); add(M * E);
         w.layer_bytes = lb;
     }
     w.layer_base = p;
@@ -159,6 +161,8 @@ extern "C" int mvn_seq_encoder_fwd(const mvn_seq_cfg* cfg, const float* params, 
     const int M = c.B * c.T, E = c.E, F = c.ff_mult * c.E;
     const int32_t* nrows = w.cu + c.B;
     const float scale = 1.0f / sqrtf((float)E);
+    const int gp = c.prec >= 1 ? 1 : 0;                                   // precision of the per-op GEMM / attention launches
+    const bool fuse_ffn = c.prec == 2 && ffn_fused_supported(E, c.ff_mult);  // prec 2: h stays on chip (ffn_fused.cu)
 
     MVN_TRY(mvn_pack_plan(mask, c.B, c.T, 1, w.cu, w.tok_src, w.keyvalid, st));
     // dropout sites (src/transformer_utils.py:147,112,115): 0 = transformer input, 1+2l = after norm1, 2+2l = after norm2 of layer l
@@ -169,19 +173,25 @@ extern "C" int mvn_seq_encoder_fwd(const mvn_seq_cfg* cfg, const float* params, 
         const float* P = params + o.layer0 + (size_t)l * o.layer_stride;
         const LayerBuf lb = w.layer(l);
         GemmEpilogue e0;
-        MVN_TRY(launch_gemm(xin, P + o.wqkv, lb.qkv, nrows, M, 3 * E, E, true, e0, c.prec, st));
-        MVN_TRY(mvn_attention_fwd(lb.qkv, w.cu, nullptr, lb.att, lb.lse, c.B, E, c.H, scale, c.prec, st));
+        MVN_TRY(launch_gemm(xin, P + o.wqkv, lb.qkv, nrows, M, 3 * E, E, true, e0, gp, st));
+        MVN_TRY(mvn_attention_fwd(lb.qkv, w.cu, nullptr, lb.att, lb.lse, c.B, E, c.H, scale, gp, st));
         GemmEpilogue e1;
         e1.bias = P + o.bu; e1.addend = xin; e1.gamma = P + o.g1; e1.beta = P + o.b1n; e1.xhat = lb.xhat1; e1.rstd = lb.rstd1; e1.eps = c.ln_eps;
         e1.drop = make_drop(c.dropout_p, c.seed, 1 + 2 * l);
-        MVN_TRY(launch_gemm(lb.att, P + o.wu, lb.x1, nrows, M, E, E, true, e1, c.prec, st));
+        MVN_TRY(launch_gemm(lb.att, P + o.wu, lb.x1, nrows, M, E, E, true, e1, gp, st));
+        if (fuse_ffn) {
+            MVN_TRY(launch_ffn_fused_fwd(lb.x1, P + o.w1, P + o.b1, P + o.w2, P + o.b2, P + o.g2, P + o.b2n, lb.x2, lb.xhat2, lb.rstd2, nrows, M, E,
+                                         c.ln_eps, make_drop(c.dropout_p, c.seed, 2 + 2 * l), st));
+            xin = lb.x2;
+            continue;
+        }
         GemmEpilogue e2;
         e2.bias = P + o.b1; e2.act = MVN_ACT_RELU;
-        MVN_TRY(launch_gemm(lb.x1, P + o.w1, lb.h, nrows, M, F, E, true, e2, c.prec, st));
+        MVN_TRY(launch_gemm(lb.x1, P + o.w1, lb.h, nrows, M, F, E, true, e2, gp, st));
         GemmEpilogue e3;
         e3.bias = P + o.b2; e3.addend = lb.x1; e3.gamma = P + o.g2; e3.beta = P + o.b2n; e3.xhat = lb.xhat2; e3.rstd = lb.rstd2; e3.eps = c.ln_eps;
         e3.drop = make_drop(c.dropout_p, c.seed, 2 + 2 * l);
-        MVN_TRY(launch_gemm(lb.h, P + o.w2, lb.x2, nrows, M, E, F, true, e3, c.prec, st));
+        MVN_TRY(launch_gemm(lb.h, P + o.w2, lb.x2, nrows, M, E, F, true, e3, gp, st));
         xin = lb.x2;
     }
     if (c.agg == MVN_AGG_NONE) return mvn_unpack_rows(xin, w.tok_src, nullptr, nrows, M, E, out, st);
@@ -221,6 +231,8 @@ extern "C" int mvn_seq_encoder_bwd(const mvn_seq_cfg* cfg, const float* params, 
     const int M = c.B * c.T, E = c.E, F = c.ff_mult * c.E;
     const int32_t* nrows = w.cu + c.B;
     const float scale = 1.0f / sqrtf((float)E);
+    const int gp = c.prec >= 1 ? 1 : 0;
+    const bool fuse_ffn = c.prec == 2 && ffn_fused_supported(E, c.ff_mult);
     float* part = w.partial;
     const size_t ps = w.pstride;
 
@@ -254,30 +266,36 @@ extern "C" int mvn_seq_encoder_bwd(const mvn_seq_cfg* cfg, const float* params, 
         const float* P = params + o.layer0 + (size_t)l * o.layer_stride;
         const LayerBuf lb = w.layer(l);
         const float* xin = l > 0 ? w.layer(l - 1).x2 : w.x0;
+        if (fuse_ffn) {
+            // norm2 backward + ff.2 / ff.0 input and weight gradients in one kernel; h is recomputed from x1 on chip
+            MVN_TRY(launch_ffn_fused_bwd(w.dX, lb.xhat2, lb.rstd2, lb.x1, P + o.w1, P + o.b1, P + o.w2, P + o.g2, w.dA, nrows, M, E,
+                                         make_drop(c.dropout_p, c.seed, 2 + 2 * l), part, ps, o.w1, o.b1, o.w2, o.b2, o.g2, o.b2n, st));
+        } else {
         // norm2 backward: dX (grad of x2) -> dz2 in w.dz
         MVN_TRY(launch_ln_bwd(w.dX, lb.xhat2, lb.rstd2, P + o.g2, w.dz, nrows, M, E, part, ps, o.g2, o.b2n, st, make_drop(c.dropout_p, c.seed, 2 + 2 * l)));
         // ff.2: dW2 = dz2^T h ; dh = (dz2 W2) * relu'(h)
-        MVN_TRY(launch_wgrad_partials(w.dz, lb.h, nrows, M, E, F, part, ps, o.w2, (long long)o.b2, c.prec, st));
+        MVN_TRY(launch_wgrad_partials(w.dz, lb.h, nrows, M, E, F, part, ps, o.w2, (long long)o.b2, gp, st));
         GemmEpilogue eh;
         eh.act_src = lb.h; eh.dact = 1;
-        MVN_TRY(launch_gemm(w.dz, P + o.w2, w.dh, nrows, M, F, E, false, eh, c.prec, st));
+        MVN_TRY(launch_gemm(w.dz, P + o.w2, w.dh, nrows, M, F, E, false, eh, gp, st));
         // ff.0: dW1 = dh^T x1 ; dx1 = dh W1 + dz2 (residual)
-        MVN_TRY(launch_wgrad_partials(w.dh, lb.x1, nrows, M, F, E, part, ps, o.w1, (long long)o.b1, c.prec, st));
+        MVN_TRY(launch_wgrad_partials(w.dh, lb.x1, nrows, M, F, E, part, ps, o.w1, (long long)o.b1, gp, st));
         GemmEpilogue e1;
         e1.addend = w.dz;
-        MVN_TRY(launch_gemm(w.dh, P + o.w1, w.dA, nrows, M, E, F, false, e1, c.prec, st));
+        MVN_TRY(launch_gemm(w.dh, P + o.w1, w.dA, nrows, M, E, F, false, e1, gp, st));
+        }
         // norm1 backward: dA -> dz1 in w.dz
         MVN_TRY(launch_ln_bwd(w.dA, lb.xhat1, lb.rstd1, P + o.g1, w.dz, nrows, M, E, part, ps, o.g1, o.b1n, st, make_drop(c.dropout_p, c.seed, 1 + 2 * l)));
         // unifyheads: dWu = dz1^T att ; datt = dz1 Wu  (into w.dA)
-        MVN_TRY(launch_wgrad_partials(w.dz, lb.att, nrows, M, E, E, part, ps, o.wu, (long long)o.bu, c.prec, st));
+        MVN_TRY(launch_wgrad_partials(w.dz, lb.att, nrows, M, E, E, part, ps, o.wu, (long long)o.bu, gp, st));
         GemmEpilogue e2;
-        MVN_TRY(launch_gemm(w.dz, P + o.wu, w.dA, nrows, M, E, E, false, e2, c.prec, st));
-        MVN_TRY(mvn_attention_bwd(lb.qkv, w.cu, nullptr, lb.att, lb.lse, w.dA, w.dqkv, c.B, E, c.H, scale, c.prec, st));
+        MVN_TRY(launch_gemm(w.dz, P + o.wu, w.dA, nrows, M, E, E, false, e2, gp, st));
+        MVN_TRY(mvn_attention_bwd(lb.qkv, w.cu, nullptr, lb.att, lb.lse, w.dA, w.dqkv, c.B, E, c.H, scale, gp, st));
         // q/k/v projections: dWqkv = dqkv^T xin ; dxin = dqkv Wqkv + dz1 (residual) -> w.dX
-        MVN_TRY(launch_wgrad_partials(w.dqkv, xin, nrows, M, 3 * E, E, part, ps, o.wqkv, -1, c.prec, st));
+        MVN_TRY(launch_wgrad_partials(w.dqkv, xin, nrows, M, 3 * E, E, part, ps, o.wqkv, -1, gp, st));
         GemmEpilogue e3;
         e3.addend = w.dz;
-        MVN_TRY(launch_gemm(w.dqkv, P + o.wqkv, w.dX, nrows, M, E, 3 * E, false, e3, c.prec, st));
+        MVN_TRY(launch_gemm(w.dqkv, P + o.wqkv, w.dX, nrows, M, E, 3 * E, false, e3, gp, st));
         MVN_TRY(launch_reduce_partials(part, ps, o.layer_stride, grads + o.layer0 + (size_t)l * o.layer_stride, 0, st));
     }
     // embedding_mag / band_emb

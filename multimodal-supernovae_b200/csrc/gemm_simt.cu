@@ -273,10 +273,11 @@ int launch_gemm(const float* A, const float* Bm, float* C, const int32_t* n_rows
                 bool b_is_nk, const GemmEpilogue& ep, int prec, cudaStream_t st) {
     MVN_CHECK_ARG(A && Bm && C && M_cap > 0 && N > 0 && K > 0, "gemm: null pointer or non-positive size (M=%d N=%d K=%d)", M_cap, N, K);
     ProfScope prof(PROF_GEMM, st);
-    if (prec == 1 && !(ep.drop.thresh && !ep.gamma)) {     // the tensor-core epilogue applies dropout only after LayerNorm
+    if (prec >= 1 && !(ep.drop.thresh && !ep.gamma)) {     // the tensor-core epilogue applies dropout only after LayerNorm
         int r = launch_gemm_tc(A, Bm, C, n_rows_dev, M_cap, N, K, b_is_nk, ep, st);
-        if (r != MVN_E_UNSUPPORTED) return r;     // shapes the tensor-core kernel does not cover use the FFMA kernel
+        if (r != MVN_E_UNSUPPORTED) { if (r == 0) count_tier(TIER_TC); return r; }     // shapes the tensor-core kernel does not cover use the FFMA kernel
     }
+    count_tier(TIER_FFMA);
     GemmArgs a;
     a.A = A; a.B = Bm; a.C = C; a.n_rows_dev = n_rows_dev; a.M_cap = M_cap; a.N = N; a.K = K; a.b_is_nk = b_is_nk ? 1 : 0;
     a.vecA = (K % 4 == 0) && aligned16(A);
@@ -304,10 +305,11 @@ int launch_wgrad_partials(const float* dY, const float* X, const int32_t* n_rows
                           float* partial, size_t pstride, size_t woff, long long boff, int prec, cudaStream_t st) {
     MVN_CHECK_ARG(dY && X && partial && M_cap > 0 && N > 0 && K > 0, "wgrad: null pointer or non-positive size");
     ProfScope prof(PROF_WGRAD, st);
-    if (prec == 1) {
+    if (prec >= 1) {
         const int r = launch_wgrad_tc(dY, X, n_rows_dev, M_cap, N, K, partial, pstride, woff, boff, st);
-        if (r != MVN_E_UNSUPPORTED) return r;
+        if (r != MVN_E_UNSUPPORTED) { if (r == 0) count_tier(TIER_TC); return r; }
     }
+    count_tier(TIER_FFMA);
     dim3 grid(kSlabs, cdiv(N, 64), cdiv(K, 64));
     wgrad_kernel<<<grid, 256, 0, st>>>(dY, X, n_rows_dev, M_cap, N, K, partial, pstride, woff, boff,
                                        (N % 4 == 0) && aligned16(dY), (K % 4 == 0) && aligned16(X));

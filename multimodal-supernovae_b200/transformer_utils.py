@@ -17,7 +17,7 @@ from . import _lib, ops
 from ._lib import SeqCfg
 
 _AGG = {"mean": _lib.MVN_AGG_MEAN, "max": _lib.MVN_AGG_MAX, "pretraining": _lib.MVN_AGG_NONE, "attn": _lib.MVN_AGG_NONE}
-_PREC = {"fp32": 0, "tf32": 1}
+_PREC = {"fp32": 0, "tf32": 1, "fused": 2}
 
 
 def _prec_of(module) -> int:
@@ -25,7 +25,9 @@ def _prec_of(module) -> int:
 
 
 def set_precision(module: nn.Module, precision: str) -> nn.Module:
-    """precision in {'fp32','tf32'}: arithmetic tier of every maven_b200 submodule (storage stays fp32)."""
+    """precision in {'fp32','tf32','fused'}: arithmetic tier of every maven_b200 submodule (storage stays fp32).
+    'fused' = the tf32 arithmetic with the fused block kernels of the whole-encoder call (per-layer intermediates stay on chip);
+    modules built from the per-op kernels treat it like 'tf32'."""
     if precision not in _PREC:
         raise ValueError(f"precision must be one of {list(_PREC)}, got {precision!r}")
     for m in module.modules():

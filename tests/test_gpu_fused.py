@@ -1,0 +1,154 @@
+"""GPU parity tests of the fused block kernels (prec=2 tier: TF32 warp-MMA contraction, fp32 accumulate, per-layer
+intermediates kept on chip).  References: torch fp64 autograd of the reference expressions
+(src/transformer_utils.py:101-116) and the CPU oracle.  Tolerance: 1e-3 normwise relative forward (north_star's
+reduced-precision tier), gradients 3e-3 (two chained TF32 contractions)."""
+import ctypes
+import math
+
+import pytest
+import torch
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+TOL_FWD = 1e-3
+TOL_GRAD = 3e-3
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def L():
+    from maven_b200 import _lib
+    return _lib.lib()
+
+
+def P(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def S():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ffn_ref(x, w1, b1, w2, b2, g, b, keep=None):
+    z = x + torch.relu(x @ w1.t() + b1) @ w2.t() + b2
+    y = torch.nn.functional.layer_norm(z, (x.shape[1],), g, b, 1e-5)
+    return y if keep is None else y * keep
+
+
+def _ffn_params(E, seed):
+    torch.manual_seed(seed)
+    F = 4 * E
+    return (torch.randn(F, E) / math.sqrt(E), torch.randn(F) * 0.3, torch.randn(E, F) / math.sqrt(F), torch.randn(E) * 0.3,
+            1.0 + 0.2 * torch.randn(E), 0.2 * torch.randn(E))
+
+
+@pytest.mark.parametrize("E", [32, 64])
+@pytest.mark.parametrize("M_cap,n", [(5000, 5000), (4100, 2345), (77, 77), (16, 5), (40000, 39999)])
+@pytest.mark.parametrize("p", [0.0, 0.25])
+def test_ffn_fused_fwd_bwd(L, E, M_cap, n, p):
+    """one call forward, one call backward vs torch fp64 autograd; rows past the device-side live count are untouched."""
+    w1, b1, w2, b2, g, b = _ffn_params(E, E + M_cap)
+    x = torch.randn(M_cap, E); dy = torch.randn(M_cap, E)
+    seed, site = 1234567 + M_cap, 4
+    xg, dyg = x.to(dev()), dy.to(dev())
+    pg = [t.to(dev()) for t in (w1, b1, w2, b2, g, b)]
+    nrows = torch.tensor([n], dtype=torch.int32, device=dev())
+    keep = None
+    if p > 0:
+        keep = torch.empty(M_cap, E, device=dev())
+        assert L.mvn_dropout_scale(seed, site, p, M_cap, E, P(keep), S()) == 0
+        keep = keep.cpu().double()
+        assert 0.6 < float((keep > 0).double().mean()) < 0.9
+    xr = x[:n].double().requires_grad_()
+    pr = [t.double().requires_grad_() for t in (w1, b1, w2, b2, g, b)]
+    yr = _ffn_ref(xr, *pr, keep=None if keep is None else keep[:n])
+    yr.backward(dy[:n].double())
+
+    y = torch.full((M_cap, E), 7.0, device=dev()); xhat = torch.full((M_cap, E), 7.0, device=dev()); rstd = torch.full((M_cap,), 7.0, device=dev())
+    rc = L.mvn_ffn_fused_fwd(P(xg), P(pg[0]), P(pg[1]), P(pg[2]), P(pg[3]), P(pg[4]), P(pg[5]), P(y), P(xhat), P(rstd), P(nrows), M_cap, E, 4,
+                             1e-5, p, seed, site, S())
+    assert rc == 0, L.mvn_last_error()
+    torch.cuda.synchronize()
+    assert relerr(y[:n], yr) < TOL_FWD
+    assert (y[n:] == 7.0).all() and (xhat[n:] == 7.0).all() and (rstd[n:] == 7.0).all()
+    zr = (xr + torch.relu(xr @ pr[0].t() + pr[1]) @ pr[2].t() + pr[3]).detach()
+    assert relerr(xhat[:n], (zr - zr.mean(1, keepdim=True)) / torch.sqrt(zr.var(1, unbiased=False, keepdim=True) + 1e-5)) < TOL_FWD
+    assert relerr(rstd[:n], 1 / torch.sqrt(zr.var(1, unbiased=False) + 1e-5)) < TOL_FWD
+
+    wsb = L.mvn_ffn_fused_bwd_workspace_bytes(E, 4)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev())
+    dx = torch.full((M_cap, E), 7.0, device=dev())
+    gr = [torch.full_like(t, float("nan")) for t in pg]
+    rc = L.mvn_ffn_fused_bwd(P(dyg), P(xhat), P(rstd), P(xg), P(pg[0]), P(pg[1]), P(pg[2]), P(pg[4]), P(dx), P(gr[0]), P(gr[1]), P(gr[2]), P(gr[3]),
+                             P(gr[4]), P(gr[5]), P(nrows), M_cap, E, 4, p, seed, site, P(ws), wsb, S())
+    assert rc == 0, L.mvn_last_error()
+    torch.cuda.synchronize()
+    assert (dx[n:] == 7.0).all()
+    errs = {"dx": relerr(dx[:n], xr.grad)}
+    for name, got, ref in zip(("dW1", "db1", "dW2", "db2", "dgamma", "dbeta"), gr, pr):
+        assert torch.isfinite(got).all(), name
+        errs[name] = relerr(got, ref.grad)
+    print({k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < TOL_GRAD, errs
+
+
+def test_ffn_fused_matches_unfused_tier(L):
+    """the fused pair and the layer-by-layer tcgen05 kernels agree to TF32 accuracy on the same inputs."""
+    E, M = 64, 9000
+    w1, b1, w2, b2, g, b = (t.to(dev()) for t in _ffn_params(E, 3))
+    torch.manual_seed(9)
+    x = torch.randn(M, E, device=dev())
+    y = torch.empty(M, E, device=dev()); xhat = torch.empty(M, E, device=dev()); rstd = torch.empty(M, device=dev())
+    assert L.mvn_ffn_fused_fwd(P(x), P(w1), P(b1), P(w2), P(b2), P(g), P(b), P(y), P(xhat), P(rstd), None, M, E, 4, 1e-5, 0.0, 0, 0, S()) == 0
+    h = torch.empty(M, 4 * E, device=dev()); y2 = torch.empty(M, E, device=dev()); xh2 = torch.empty(M, E, device=dev()); rs2 = torch.empty(M, device=dev())
+    assert L.mvn_linear_fwd(P(x), P(w1), P(b1), P(h), None, M, 4 * E, E, 1, 1, S()) == 0
+    assert L.mvn_linear_res_ln_fwd(P(h), P(w2), P(b2), P(x), P(g), P(b), P(y2), P(xh2), P(rs2), None, M, E, 4 * E, 1e-5, 1, S()) == 0
+    torch.cuda.synchronize()
+    assert relerr(y, y2) < TOL_FWD and relerr(xhat, xh2) < TOL_FWD and relerr(rstd, rs2) < TOL_FWD
+
+
+def test_ffn_fused_unsupported_shapes_raise(L):
+    x = torch.zeros(64, 128, device=dev())
+    rc = L.mvn_ffn_fused_fwd(P(x), P(x), None, P(x), None, P(x), P(x), P(x), None, None, None, 64, 128, 4, 1e-5, 0.0, 0, 0, S())
+    assert rc == -2 and b"emb=128" in L.mvn_last_error()
+    rc = L.mvn_ffn_fused_fwd(P(x), P(x), None, P(x), None, P(x), P(x), P(x), None, None, None, 64, 32, 6, 1e-5, 0.0, 0, 0, S())
+    assert rc == -2
+
+
+@pytest.mark.parametrize("case", ["lc", "sp"])
+def test_fused_seq_encoder_vs_oracle(L, case):
+    """Whole encoder forward + backward in the fused tier vs the fp32 oracle at the C4 shapes, and proof that the fused
+    kernels ran: tier counter 3 advanced once per layer and direction, nothing fell back to the FFMA GEMMs.
+    (Dropout on a given mask: tests/test_gpu_parity.py::test_seq_encoder_dropout_given_mask[fused].)"""
+    from maven_b200.selfcheck import synthetic_seq
+    from maven_b200.transformer_utils import TransformerWithTimeEmbeddings, set_precision
+    from oracle import maven_oracle as O
+    gen = torch.Generator().manual_seed(11)
+    if case == "lc":
+        kw = dict(n_out=32, nband=2, agg="mean", time_norm=20583.37, emb=64, heads=8, depth=5)
+        x, t, m = synthetic_seq(gen, 48, 200, 2, 300.0, 20, 100, 0.0)
+    else:
+        kw = dict(n_out=32, nband=1, agg="mean", time_norm=17945.14, emb=32, heads=2, depth=13)
+        x, t, m = synthetic_seq(gen, 48, 220, 1, 5500.0, 110, 220, 3700.0)
+    torch.manual_seed(0)
+    enc = TransformerWithTimeEmbeddings(dropout=0.0, **kw)
+    okw = {k: kw[k] for k in ("emb", "heads", "depth", "nband", "agg", "time_norm")}
+    sdg = {k: v.detach().float().requires_grad_() for k, v in enc.state_dict().items()}
+    yr = O.seq_encoder(sdg, "", x[..., None], t, m, **okw)
+    w = torch.randn(yr.shape, generator=gen)
+    (yr * w).sum().backward()
+    enc = set_precision(enc.to(dev()), "fused")
+    L.mvn_tier_reset()
+    y = enc(x[..., None].to(dev()), t.to(dev()), m.to(dev()))
+    (y * w.to(dev())).sum().backward()
+    torch.cuda.synchronize()
+    assert L.mvn_tier_count(3) >= 2 * kw["depth"], "fused kernels did not run for every layer"
+    e_fwd = relerr(y, yr)
+    worst = max((relerr(q.grad, sdg[k].grad), k) for k, q in enc.named_parameters())
+    print(f"fused tier {case}: fwd relerr {e_fwd:.3e}, worst grad relerr {worst[0]:.3e} ({worst[1]})")
+    assert e_fwd < TOL_FWD
+    assert worst[0] < 1e-2, worst

@@ -416,7 +416,7 @@ def test_retrieval_ranks():
     assert torch.equal(r.long(), O.retrieval_ranks(e1.double(), e2.double()))
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "fused"])
 def test_seq_encoder_dropout_given_mask(L, prec):
     """In-kernel dropout (Transformer input + after both LayerNorms of every block): the kernels' counter-based masks are
     read back with mvn_dropout_scale, scattered to the padded layout and injected into the oracle; forward and parameter
