@@ -91,13 +91,15 @@ def model_kwargs(wl, dropout):
     return kw
 
 
-def flops_per_step(wl, batch):
-    """Algorithmic FLOPs of one training step, two accountings: dense over the padded T (comparable with
-    the reference) and executed (valid tokens only).  Returned per kernel class for the executed accounting."""
-    out = {"padded_train": 0.0, "gemm": 0.0, "wgrad": 0.0, "attn_fwd": 0.0, "attn_bwd": 0.0,
-           "bytes": {"gemm": 0.0, "wgrad": 0.0, "attn_fwd": 0.0, "attn_bwd": 0.0, "row": 0.0, "conv": 0.0}}
+def flops_per_step(wl, batch, precision="tf32"):
+    """Algorithmic FLOPs and HBM bytes of one training step, two FLOP accountings: dense over the padded T
+    (comparable with the reference) and executed (valid tokens only; recomputation inside fused kernels is NOT credited).
+    Returned per kernel class; which class a piece of work lands in depends on the tier (`fused` moves the feed-forward
+    half of every block out of the gemm / wgrad / row classes into fused_fwd / fused_bwd)."""
+    cls = ("gemm", "wgrad", "attn_fwd", "attn_bwd", "fused_fwd", "fused_bwd", "row", "conv")
+    out = {"padded_train": 0.0, **{k: 0.0 for k in cls[:6]}, "bytes": {k: 0.0 for k in cls}}
     if wl.get("img"):
-        # ConvMixer (SURVEY §8d): ~1.1 MFLOP fwd per sample, train ~3x; bytes = the fp32 image once forward and once more for the
+        # ConvMixer (SURVEY 8d): ~1.1 MFLOP fwd per sample, train ~3x; bytes = the fp32 image once forward and once more for the
         # patch-conv weight gradient, plus the 128-B embedding
         Bn = batch[0].shape[0]
         out["padded_train"] += 3.3e6 * Bn
@@ -106,26 +108,40 @@ def flops_per_step(wl, batch):
         kw = wl[key]
         if kw is None:
             continue
-        E, L = kw["emb"], kw["depth"]
+        E, L, H = kw["emb"], kw["depth"], kw["heads"]
+        fused = precision == "fused" and E in (32, 64)
         nb = batch[m_idx].sum(dim=1).double()
         B = nb.numel()
         out["padded_train"] += 3.0 * B * L * (24.0 * T * E * E + 4.0 * T * T * E)
         M = nb.sum().item()
-        out["gemm"] += L * 48.0 * M * E * E            # forward GEMMs + input-gradient GEMMs
-        out["wgrad"] += L * 24.0 * M * E * E
         n2 = (nb * nb).sum().item()
         out["attn_fwd"] += L * 4.0 * n2 * E
         out["attn_bwd"] += L * 10.0 * n2 * E
-        # algorithmic HBM bytes (fp32 storage; every operand counted once in, once out -- DESIGN.md "bytes per token-layer"):
-        #   GEMM class  fwd qkv 4E, unify+res+LN 4E, ff1 5E, ff2+res+LN 7E; dgrad ff2 9E, ff1 6E, unify 2E, qkv 5E  = 42E floats
-        #   wgrad class ff2 5E, ff1 5E, unify 2E, qkv 4E = 16E;  attention fwd 4E+H, bwd 8E+H;  LayerNorm bwd 2 x 3E
-        H = kw["heads"]
-        out["bytes"]["gemm"] += 4.0 * L * M * 42 * E
-        out["bytes"]["wgrad"] += 4.0 * L * M * 16 * E
+        # FLOPs per token-layer: qkv 6E^2, unify 2E^2, ff1 8E^2, ff2 8E^2 forward; the same again for the input gradients and
+        # once more for the weight gradients.
+        # HBM bytes per token-layer (fp32 storage, every operand once in / once out -- DESIGN.md):
+        #   layer-by-layer: GEMM class fwd qkv 4E, unify+res+LN 4E, ff1 5E, ff2+res+LN 7E; dgrad ff2 9E, ff1 6E, unify 2E, qkv 5E (42E);
+        #                   wgrad class ff2 5E, ff1 5E, unify 2E, qkv 4E (16E); attention fwd 4E+H, bwd 8E+H; LayerNorm bwd 2 x 3E
+        #   fused FFN     : forward x1 in, x2 + xhat2 out (3E + 1); backward dy, xhat2, x1 in, dx1 out (4E + 1)
+        if fused:
+            out["gemm"] += L * 16.0 * M * E * E
+            out["wgrad"] += L * 8.0 * M * E * E
+            out["fused_fwd"] += L * 16.0 * M * E * E
+            out["fused_bwd"] += L * 32.0 * M * E * E
+            out["bytes"]["gemm"] += 4.0 * L * M * 15 * E
+            out["bytes"]["wgrad"] += 4.0 * L * M * 6 * E
+            out["bytes"]["fused_fwd"] += 4.0 * L * M * (3 * E + 1)
+            out["bytes"]["fused_bwd"] += 4.0 * L * M * (4 * E + 1)
+            out["bytes"]["row"] += 4.0 * L * M * 3 * E
+        else:
+            out["gemm"] += L * 48.0 * M * E * E
+            out["wgrad"] += L * 24.0 * M * E * E
+            out["bytes"]["gemm"] += 4.0 * L * M * 42 * E
+            out["bytes"]["wgrad"] += 4.0 * L * M * 16 * E
+            out["bytes"]["row"] += 4.0 * L * M * 6 * E
         out["bytes"]["attn_fwd"] += 4.0 * L * M * (4 * E + H)
         out["bytes"]["attn_bwd"] += 4.0 * L * M * (8 * E + H)
-        out["bytes"]["row"] += 4.0 * L * M * 6 * E
-    out["executed_train"] = out["gemm"] + out["wgrad"] + out["attn_fwd"] + out["attn_bwd"]
+    out["executed_train"] = sum(out[k] for k in cls[:6])
     return out
 
 
@@ -218,12 +234,35 @@ def peaks():
 
 
 # --------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port (reference algorithm, fp32, dense over padded T) on host cores
+# reference arm / cpu baseline: the UNMODIFIED reference (staged under oracle/_ref by oracle/build_ref.py; framework imports
+# stubbed by oracle/ref_loader.py) running its own LightCurveImageCLIP.training_step + backward + torch.optim.RAdam on the host
+# cores.  Falls back to the oracle port (same algorithm restated, oracle/maven_oracle.py) only when no reference tree travelled.
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_steps(wl, sample_B, steps, warmup, threads):
+def reference_kind():
+    from oracle import ref_loader
+    return "reference" if ref_loader.reference_root() is not None else "port"
+
+
+def make_reference_stepper(wl, dropout, device="cpu"):
+    """-> (kind, step(batch) -> loss tensor) for the reference's training step (src/models_multimodal.py:312-366 + :306-310)."""
+    kind = reference_kind()
+    if kind == "reference":
+        from oracle import ref_loader
+        _, _, rmm = ref_loader.import_reference()
+        torch.manual_seed(0)
+        model = rmm.LightCurveImageCLIP(**model_kwargs(wl, dropout)).to(device).train()
+        model.log = lambda *a, **k: None
+        opt = model.configure_optimizers()["optimizer"]             # torch.optim.RAdam(self.parameters(), lr, **optimizer_kwargs)
+
+        def step(batch):
+            loss = model.training_step(tuple(batch), 0)              # the reference's own 9-tuple batch (src/models_multimodal.py:312-324)
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            return loss
+        return kind, step
     from oracle import maven_oracle as O
     from maven_b200.models_multimodal import LightCurveImageCLIP
-    torch.set_num_threads(threads)
     torch.manual_seed(0)
     ref_model = LightCurveImageCLIP(**model_kwargs(wl, 0.0))        # used only as a weight initialiser (reference default init)
     sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in ref_model.state_dict().items()}
@@ -231,36 +270,88 @@ def cpu_reference_steps(wl, sample_B, steps, warmup, threads):
     opt = torch.optim.RAdam(params, lr=LR, weight_decay=WD)
     cfg = dict(combinations=wl["combinations"], nband=2, transformer_kwargs=wl["lc"], transformer_spectral_kwargs=wl["sp"],
                classification=wl.get("classification", False), n_classes=wl.get("n_classes", 5), conv_kwargs=CONV)
-    batch = make_batch(wl, sample_B, seed=1234)
-    times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
+
+    def step(batch):
         loss = O.training_loss(sd, cfg, batch)
         loss.backward()
         opt.step()
         opt.zero_grad(set_to_none=True)
+        return loss
+    return kind, step
+
+
+def cpu_reference_steps(wl, sample_B, steps, warmup, threads, dropout=0.0):
+    """-> (samples/s, seconds per step, kind) over `steps` timed steps at batch `sample_B` on `threads` host threads."""
+    torch.set_num_threads(threads)
+    kind, step = make_reference_stepper(wl, dropout)
+    batch = make_batch(wl, sample_B, seed=1234)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        step(batch)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    return sample_B * len(times) / sum(times), sum(times) / len(times)
+    return sample_B * len(times) / sum(times), sum(times) / len(times), kind
+
+
+def bench_config(wl, args, world):
+    """The `config` object of the JSON line: the workload, identical for the B200 arm and the reference arm."""
+    return {"workload": wl["desc"], "per_gpu_batch": args.batch, "global_batch": args.batch * world, "parallelism": f"dp{world}",
+            "dropout": args.dropout, "data": "SURVEY 8d synthetic generator, seeded on the CPU"}
 
 
 def run_reference(args):
+    """Reference arm: rank 0 alone times the reference's CPU training step on all host cores; each step is a bounded sample
+    (a smaller batch) of the B200 arm's workload, sized from a probe step so that the whole run ends within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
     threads = os.cpu_count() or 1
     B = args.ref_batch
-    sps, sec = cpu_reference_steps(wl, B, args.steps, args.warmup, threads)
+    if B <= 0:
+        probe_B = 64
+        sps_probe, _, _ = cpu_reference_steps(wl, probe_B, 1, 1, threads, args.dropout)
+        budget_s = 150.0
+        B = int(budget_s * sps_probe / max(args.steps + args.warmup, 1))
+        B = max(32, min(args.batch, 1 << (B.bit_length() - 1) if B > 0 else 32))      # power of two <= the B200 arm's batch
+    sps, sec, kind = cpu_reference_steps(wl, B, args.steps, args.warmup, threads, args.dropout)
+    what = ("unmodified reference LightCurveImageCLIP.training_step + backward + torch.optim.RAdam (oracle/_ref, framework imports stubbed)"
+            if kind == "reference" else "oracle port of the reference algorithm (no reference tree on this box)")
     line = {"impl": "reference", "metric": "clip_train_samples_per_sec", "value": sps, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "per_step_batch": B, "note": "oracle port of the reference algorithm (dense over padded T), torch CPU"},
-            "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
-                             "sample": f"{args.steps} training steps (fwd+bwd+torch RAdam) at batch {B} of the same workload"},
+            "config": bench_config(wl, args, args.gpus),
+            "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": kind,
+                             "sample": f"{args.steps} training steps at batch {B} (a bounded sample of the per-GPU batch {args.batch}), fp32, "
+                                       f"dense over the padded T, dropout {args.dropout}: {what}"},
             "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
+
+
+def reference_eager_on_gpu(wl, dropout, dev, B=256, steps=3):
+    """Context figure: what a user of the reference gets on this GPU today -- the unmodified modules run eagerly
+    by PyTorch on cuda (cuBLAS/ATen kernels, ~16.6k launches per step), fp32 and with TF32 matmuls allowed."""
+    if reference_kind() != "reference":
+        return None
+    out = {"batch": B, "steps": steps}
+    batch = [None if v is None else v.to(dev) for v in make_batch(wl, B, seed=1234)]
+    for name, allow in (("fp32", False), ("tf32", True)):
+        torch.backends.cuda.matmul.allow_tf32 = allow
+        torch.backends.cudnn.allow_tf32 = allow
+        _, step = make_reference_stepper(wl, dropout, device=dev)
+        for _ in range(2):
+            step(batch)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step(batch)
+        torch.cuda.synchronize()
+        out[name + "_samples_per_s"] = B * steps / (time.perf_counter() - t0)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -290,7 +381,7 @@ def run_gpu(args):
     pinned = [None if v is None else v.pin_memory() for v in host]
     resident = [None if v is None else v.to(dev) for v in host]
     h2d = sum(v.numel() * v.element_size() for v in pinned if v is not None)      # every tensor of the 9-tuple batch is copied per step
-    fl = flops_per_step(wl, host)
+    fl = flops_per_step(wl, host, args.precision)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
 
     def step(batch):
@@ -372,8 +463,6 @@ def run_gpu(args):
     else:
         def run_step(batch):
             return step(resident if batch is None else batch)
-    top = max(("gemm", "wgrad", "attn_fwd", "attn_bwd", "row"), key=lambda k: breakdown[k]["ms"])
-    ms_t, cnt_t = ctypes.c_double(prof_tot[top][0]), ctypes.c_longlong(prof_tot[top][1])
 
     # ---- timed region: K steps, device-resident inputs, per-step CUDA events, L2 flushed between steps ----
     import gc
@@ -444,62 +533,84 @@ def run_gpu(args):
     ms_per_step = dev_ms / args.steps
     value = world * B * args.steps / (dev_ms / 1e3)
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
-    hbm_bound = top in ("gemm", "wgrad", "row")          # token-stream kernels: K,N <= 256 -> bytes, not flops, bound them
-    n_l = max(cnt_t.value, 1)
-    avg_ms = ms_t.value / n_l                              # average launch duration of the class inside the timed region
-    if hbm_bound:
-        per_launch = fl["bytes"][top] * args.steps / n_l   # algorithmic bytes per launch (class average)
-        ach, peak, unit = per_launch / (avg_ms / 1e3) / 1e9, hbm, "GB/s"
-    else:
-        per_launch = fl[top] * args.steps / n_l
-        ach, peak, unit = per_launch / (avg_ms / 1e3) / 1e12, tf, "TFLOP/s"
-    traffic = None
+    # ---- roofline, SURVEY 8(d): the encoder blocks and the similarity are tensor-class (fraction = FLOPs / time / sustained
+    # bf16 peak), embed / LayerNorm-backward / pool / ConvMixer are HBM-class (fraction = algorithmic bytes / time / copy peak).
+    # Every class reports BOTH fractions; `roofline` is the class with the most device time inside the step.
+    tensor_classes = ("gemm", "wgrad", "attn_fwd", "attn_bwd", "fused_fwd", "fused_bwd")
+    traffic_all = {}
     tpath = os.path.join(ROOT, "profiles", "traffic_per_launch.json")   # from the committed ncu --set full capture (scripts/ncu_summary.py)
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(args.precision, {}).get(top)
+        traffic_all = json.load(open(tpath))
     classes = {}
-    for k in ("gemm", "wgrad", "attn_fwd", "attn_bwd", "row", "conv"):
-        ms_k = breakdown[k]["ms"]
-        if ms_k > 0:
-            classes[k] = {"ms": ms_k, "algorithmic_GBps": fl["bytes"][k] / (ms_k / 1e3) / 1e9, "frac_hbm": fl["bytes"][k] / (ms_k / 1e3) / 1e9 / hbm}
-            if k in fl and k != "row":
-                classes[k]["executed_TFLOPs"] = fl[k] / (ms_k / 1e3) / 1e12
-    cpu = None
+    for k in ("gemm", "wgrad", "attn_fwd", "attn_bwd", "fused_fwd", "fused_bwd", "row", "conv"):
+        ms_k, n_k = breakdown[k]["ms"], breakdown[k]["launches"]
+        if ms_k <= 0:
+            continue
+        c = {"ms": ms_k, "launches": n_k, "bound": "tensor" if k in tensor_classes else "hbm",
+             "algorithmic_GBps": fl["bytes"][k] / (ms_k / 1e3) / 1e9, "frac_hbm": fl["bytes"][k] / (ms_k / 1e3) / 1e9 / hbm}
+        if k in tensor_classes:
+            c["executed_TFLOPs"] = fl[k] / (ms_k / 1e3) / 1e12
+            c["frac_tensor"] = c["executed_TFLOPs"] / tf
+        classes[k] = c
+    top = max(classes, key=lambda k: classes[k]["ms"])
+    ct = classes[top]
+    n_l = max(prof_tot[top][1], 1)
+    avg_ms = prof_tot[top][0] / n_l                         # average launch duration of the class inside the timed region
+    if ct["bound"] == "tensor":
+        per_launch, ach, peak, unit = fl[top] * args.steps / n_l, ct["executed_TFLOPs"], tf, "TFLOP/s"
+    else:
+        per_launch, ach, peak, unit = fl["bytes"][top] * args.steps / n_l, ct["algorithmic_GBps"], hbm, "GB/s"
+    cpu = ref_gpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        n_cpu = 40                                              # ~10 s of host work at batch 64 on 16 cores (a bounded sample of the workload)
-        sps, sec = cpu_reference_steps(wl, args.ref_batch, n_cpu, 2, threads)
-        cpu = {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
-               "sample": f"{n_cpu} training steps (fwd+bwd+torch RAdam) at batch {args.ref_batch} of the same workload, oracle port, fp32, dense over padded T"}
+        cb, n_cpu = 128, 6                                      # ~10-30 s of host work: a bounded sample of the workload
+        sps, sec, kind = cpu_reference_steps(wl, cb, n_cpu, 1, threads, args.dropout)
+        sps1, _, _ = cpu_reference_steps(wl, 16, 2, 1, 1, args.dropout)
+        torch.set_num_threads(threads)
+        cpu = {"value": sps, "unit": "samples/s", "cores": threads, "kind": kind,
+               "sample": f"{n_cpu} training steps at batch {cb} of the same workload (fp32, dense over padded T, dropout {args.dropout}): "
+                         + ("unmodified reference training_step + backward + torch RAdam (oracle/_ref)" if kind == "reference" else "oracle port"),
+               "one_thread": {"value": sps1, "unit": "samples/s", "cores": 1, "sample": "2 steps at batch 16"}}
+        try:
+            ref_gpu = reference_eager_on_gpu(wl, args.dropout, dev)
+        except Exception as e:                                 # context only: never fails the bench line
+            ref_gpu = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
+    tr = traffic_all.get(args.precision, {})
+    step_padded = fl["padded_train"] / (ms_per_step / 1e3) / 1e12
     line = {
         "metric": "clip_train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if args.precision == "fp32" else args.precision, "data": "synthetic",
-        "config": {"workload": wl["desc"], "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                   "dropout": args.dropout, "precision": args.precision,
-                   "streams": "one CUDA stream per modality encoder" if concurrent and len(wl["combinations"]) > 1 else "single stream",
-                   "e2e_image_upload": "uint8 pixels, converted on the device (maven_b200.augment)" if img_u8 is not None else None,
-                   "launch": "whole step replayed as one CUDA graph (maven_b200.graph.GraphedTrainStep)" if graphed is not None
-                             else (graph_note or "eager launches"),
-                   "l2": "256 MiB flush written between timed steps; per-step activation working set is GBs (>> 126 MB L2)",
-                   "valid_token_fraction": {"lc": float(host[3].float().mean()), "sp": float(host[6].float().mean()) if host[6] is not None else None}},
+        "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
+        "config": bench_config(wl, args, world),
+        "runtime": {"precision": args.precision,
+                    "streams": "one CUDA stream per modality encoder" if concurrent and len(wl["combinations"]) > 1 else "single stream",
+                    "e2e_image_upload": "uint8 pixels, converted on the device (maven_b200.augment)" if img_u8 is not None else None,
+                    "launch": "whole step replayed as one CUDA graph (maven_b200.graph.GraphedTrainStep)" if graphed is not None
+                              else (graph_note or "eager launches"),
+                    "l2": "256 MiB flush written between timed steps; per-step activation working set is GBs (>> 126 MB L2)",
+                    "valid_token_fraction": {"lc": float(host[3].float().mean()), "sp": float(host[6].float().mean()) if host[6] is not None else None}},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm" if hbm_bound else "tensor", "kernel_class": top, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                     "traffic": traffic, "algorithmic_per_launch": per_launch, "avg_launch_ms": avg_ms, "peak_source": src,
-                     "launches_timed": cnt_t.value, "class_ms_per_step": ms_t.value / args.steps,
+        "roofline": {"bound": ct["bound"], "kernel_class": top, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                     "traffic": tr.get(top), "traffic_source": traffic_all.get("_source"),
+                     "algorithmic_per_launch": per_launch, "avg_launch_ms": avg_ms, "peak_source": src,
+                     "frac_hbm": ct["frac_hbm"], "launches_timed": prof_tot[top][1], "class_ms_per_step": ct["ms"],
+                     "step_frac_of_tensor_peak": {"padded": step_padded / tf, "executed": fl["executed_train"] / (ms_per_step / 1e3) / 1e12 / tf,
+                                                  "formula": "samples/s x FLOP/sample / sustained bf16 peak (SURVEY 8d); padded = dense over the padded T, "
+                                                             "executed = valid tokens only, recomputation not credited"},
                      "timing": f"CUDA events around every launch of the class over {args.steps} steps run right before the throughput region",
-                     "accounting": "class average over its launches in the timed region; executed work (valid tokens only); "
-                                   "padded-equivalent step FLOPs in flops_per_step.padded_train"},
+                     "accounting": "class average over its launches in the timed region; executed work (valid tokens only)"},
         "kernel_classes": classes,
         "flops_per_step": {k: v for k, v in fl.items() if k != "bytes"},
-        "bytes_per_step": fl["bytes"],
-        "step_tflops": {"padded_equivalent": fl["padded_train"] / (ms_per_step / 1e3) / 1e12, "executed": fl["executed_train"] / (ms_per_step / 1e3) / 1e12,
-                        "frac_of_peak_padded": fl["padded_train"] / (ms_per_step / 1e3) / 1e12 / tf},
+        "bytes_per_step": dict(fl["bytes"], total=sum(fl["bytes"].values())),
+        "step_tflops": {"padded_equivalent": step_padded, "executed": fl["executed_train"] / (ms_per_step / 1e3) / 1e12,
+                        "frac_of_peak_padded": step_padded / tf},
         "kernel_breakdown_ms": breakdown,
         "wall_s_timed_region": wall, "loss_last": last, "step_ms_rank0": [round(x, 3) for x in step_ms],
     }
+    if ref_gpu is not None:
+        line["reference_eager_b200"] = ref_gpu
     if cpu is not None:
         line["cpu_baseline"] = cpu
     emit(line)
@@ -529,7 +640,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=1024, help="samples per GPU per step")
-    ap.add_argument("--ref-batch", type=int, default=64, help="samples per CPU reference step (bounded sample)")
+    ap.add_argument("--ref-batch", type=int, default=0, help="samples per CPU reference step (0: sized from a probe step so the run ends within a few minutes)")
     ap.add_argument("--dropout", type=float, default=0.00021844858312997214,
                     help="transformer dropout p (default: pretrain_config/maven_pretrain_config.yaml); the CPU reference arm uses 0")
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "fused"],

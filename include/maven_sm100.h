@@ -312,6 +312,10 @@ void mvn_set_step_counter(const uint32_t* dev_counter);
 
 /* N3: retrieval rank of the true partner, count_i[cos(e1_i,e2_j) > cos(e1_j,e2_j)].  src/utils.py:380-426. */
 int mvn_retrieval_ranks(const float* e1, const float* e2, int N, int D, int32_t* ranks, void* stream);
+/* N3: the ROC-like curve of get_ROC_data (src/utils.py:395-413): counts[t] = #{sources j : ranks[j] < k_thr[t]}, i.e. how many true
+ * partners sit inside the top int(threshold_t * N) of their source's similarity ranking.  k_thr[n_thr] are those integer
+ * cut-offs (formed by the caller exactly like the reference: int(threshold * N) in double precision).  counts is overwritten. */
+int mvn_retrieval_curve(const int32_t* ranks, int N, const int32_t* k_thr, int n_thr, int32_t* counts, void* stream);
 
 #ifdef __cplusplus
 }

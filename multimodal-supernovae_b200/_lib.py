@@ -85,6 +85,7 @@ _SIGS = {
     "mvn_radam_step_dev": (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, P, P, P]),
     "mvn_set_step_counter": (None, [P]),
     "mvn_retrieval_ranks": (c_int, [P, P, c_int, c_int, P, P]),
+    "mvn_retrieval_curve": (c_int, [P, c_int, P, c_int, P, P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
 

@@ -110,7 +110,7 @@ class DeviceAugment:
     """NoisyDataLoader.__iter__'s per-batch work on the GPU: raw dataset tuple in, the 9-tuple of training_step out."""
 
     def __init__(self, combinations: Sequence[str], max_noise_intensity: float, noise_level_mag: float, seed: int = 0):
-        key = frozenset(combinations)
+        key = frozenset(c for c in combinations if c != "meta")     # the reference strips 'meta' before dispatch (src/dataloader.py:72-75)
         if key not in _FIELDS:
             raise ValueError(f"DeviceAugment: unsupported combination set {sorted(key)}")
         self.fields = _FIELDS[key]

@@ -19,6 +19,8 @@
 //   C(16x8): c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1).
 // An accumulator tile is reused as an A operand without shuffles by relabelling the contraction index
 // (slot t <-> column 2t, slot t+4 <-> column 2t+1): a = {c0, c2, c1, c3}, and the B side reads rows 2t, 2t+1.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mvn {
@@ -61,24 +63,24 @@ struct FfnGeom {
     static constexpr size_t SMEM_BWD = (size_t)(W_FLOATS + VEC_FLOATS + TILE_FLOATS) * 4;
 };
 
-template <int E>
+template <int E, int NTHR>
 __device__ __forceinline__ void stage_weights(float* W1s, float* W2s, float* vec, const float* __restrict__ W1, const float* __restrict__ b1,
                                               const float* __restrict__ W2, const float* __restrict__ b2, const float* __restrict__ gamma,
                                               const float* __restrict__ beta) {
     using G = FfnGeom<E>;
     constexpr int F = G::F;
-    for (int i = threadIdx.x; i < F * E / 4; i += FF_THREADS) {
+    for (int i = threadIdx.x; i < F * E / 4; i += NTHR) {
         const int f = i / (E / 4), e = (i % (E / 4)) * 4;
         const float4 v = __ldg(reinterpret_cast<const float4*>(W1) + i);
         *reinterpret_cast<float4*>(W1s + f * G::P1 + e) = make_float4(tf32r(v.x), tf32r(v.y), tf32r(v.z), tf32r(v.w));
     }
-    for (int i = threadIdx.x; i < E * F / 4; i += FF_THREADS) {
+    for (int i = threadIdx.x; i < E * F / 4; i += NTHR) {
         const int e = i / (F / 4), f = (i % (F / 4)) * 4;
         const float4 v = __ldg(reinterpret_cast<const float4*>(W2) + i);
         *reinterpret_cast<float4*>(W2s + e * G::P2 + f) = make_float4(tf32r(v.x), tf32r(v.y), tf32r(v.z), tf32r(v.w));
     }
-    for (int i = threadIdx.x; i < F; i += FF_THREADS) vec[i] = b1 ? b1[i] : 0.f;
-    for (int i = threadIdx.x; i < E; i += FF_THREADS) {
+    for (int i = threadIdx.x; i < F; i += NTHR) vec[i] = b1 ? b1[i] : 0.f;
+    for (int i = threadIdx.x; i < E; i += NTHR) {
         vec[F + i] = b2 ? b2[i] : 0.f;
         vec[F + E + i] = gamma ? gamma[i] : 1.f;
         vec[F + 2 * E + i] = beta ? beta[i] : 0.f;
@@ -94,100 +96,127 @@ struct FfnFwdArgs {
     DropCfg drop;
 };
 
-// Every warp owns 16-row blocks of the packed token stream (no cross-warp dependency after the weights are staged).
-template <int E>
-__global__ void __launch_bounds__(FF_THREADS, 1) ffn_fwd_kernel(const FfnFwdArgs a) {
+// Every warp owns blocks of 16 * MT rows of the packed token stream (no cross-warp dependency after the weights are staged);
+// MT = 2 halves the shared-memory traffic per MMA (each weight fragment feeds two row tiles).
+template <int E, int MT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) ffn_fwd_kernel(const FfnFwdArgs a) {
     using G = FfnGeom<E>;
-    constexpr int F = G::F, KS = E / 8, NT = E / 8, NC = F / 8, P1 = G::P1, P2 = G::P2;
+    constexpr int F = G::F, KS = E / 8, NT = E / 8, NC = F / 8, P1 = G::P1, P2 = G::P2, RPB = 16 * MT;
     extern __shared__ __align__(16) float smem_f[];
     float* W1s = smem_f;
     float* W2s = W1s + F * P1;
     float* vec = W2s + E * P2;
     pdl_trigger();
-    stage_weights<E>(W1s, W2s, vec, a.W1, a.b1, a.W2, a.b2, a.gamma, a.beta);
+    stage_weights<E, WARPS * 32>(W1s, W2s, vec, a.W1, a.b1, a.W2, a.b2, a.gamma, a.beta);
     __syncthreads();
     pdl_wait();                                              // weights are parameters; the token stream is the predecessor's output
     const int rows = a.n_rows_dev ? min(__ldg(a.n_rows_dev), a.M_cap) : a.M_cap;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int nblk = (rows + 15) >> 4;
+    const int nblk = (rows + RPB - 1) / RPB;
     const float* b1s = vec; const float* b2s = vec + F; const float* gs = vec + F + E; const float* bs = vec + F + 2 * E;
     const float inv_e = 1.0f / (float)E;
 
-    for (int blk = blockIdx.x * FF_WARPS + warp; blk < nblk; blk += gridDim.x * FF_WARPS) {
-        const int r_lo = blk * 16 + g, r_hi = r_lo + 8;
-        const bool v_lo = r_lo < rows, v_hi = r_hi < rows;
-        const float* x_lo = a.X + (size_t)r_lo * E;
-        const float* x_hi = a.X + (size_t)r_hi * E;
-        float xa[KS][4];
+    // block -> (CTA-minor) warp: the blocks of the last, partial round are spread over all SMs instead of filling a few CTAs
+    for (int blk = warp * gridDim.x + blockIdx.x; blk < nblk; blk += gridDim.x * WARPS) {
+        float xa[MT][KS][4];
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            xa[ks][0] = v_lo ? tf32r(__ldg(x_lo + 8 * ks + t)) : 0.f;
-            xa[ks][1] = v_hi ? tf32r(__ldg(x_hi + 8 * ks + t)) : 0.f;
-            xa[ks][2] = v_lo ? tf32r(__ldg(x_lo + 8 * ks + t + 4)) : 0.f;
-            xa[ks][3] = v_hi ? tf32r(__ldg(x_hi + 8 * ks + t + 4)) : 0.f;
+        for (int m = 0; m < MT; ++m) {
+            const int r_lo = blk * RPB + 16 * m + g, r_hi = r_lo + 8;
+            const bool v_lo = r_lo < rows, v_hi = r_hi < rows;
+            const float* x_lo = a.X + (size_t)r_lo * E;
+            const float* x_hi = a.X + (size_t)r_hi * E;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                xa[m][ks][0] = v_lo ? tf32r(__ldg(x_lo + 8 * ks + t)) : 0.f;
+                xa[m][ks][1] = v_hi ? tf32r(__ldg(x_hi + 8 * ks + t)) : 0.f;
+                xa[m][ks][2] = v_lo ? tf32r(__ldg(x_lo + 8 * ks + t + 4)) : 0.f;
+                xa[m][ks][3] = v_hi ? tf32r(__ldg(x_hi + 8 * ks + t + 4)) : 0.f;
+            }
         }
-        float o[NT][4];
+        float o[MT][NT][4];
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) o[m][nt][0] = o[m][nt][1] = o[m][nt][2] = o[m][nt][3] = 0.f;
 #pragma unroll 2
         for (int c = 0; c < NC; ++c) {
-            float hc[4];
-            hc[0] = hc[2] = b1s[8 * c + 2 * t];
-            hc[1] = hc[3] = b1s[8 * c + 2 * t + 1];
+            float hc[MT][4];
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                hc[m][0] = hc[m][2] = b1s[8 * c + 2 * t];
+                hc[m][1] = hc[m][3] = b1s[8 * c + 2 * t + 1];
+            }
             const float* w1p = W1s + (8 * c + g) * P1 + t;
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks) mma_tf32(hc, xa[ks], w1p[8 * ks], w1p[8 * ks + 4]);
-            const float ha[4] = {tf32r(fmaxf(hc[0], 0.f)), tf32r(fmaxf(hc[2], 0.f)), tf32r(fmaxf(hc[1], 0.f)), tf32r(fmaxf(hc[3], 0.f))};
+            for (int ks = 0; ks < KS; ++ks) {
+                const float b0 = w1p[8 * ks], b1v = w1p[8 * ks + 4];
+#pragma unroll
+                for (int m = 0; m < MT; ++m) mma_tf32(hc[m], xa[m][ks], b0, b1v);
+            }
+            float ha[MT][4];
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                ha[m][0] = tf32r(fmaxf(hc[m][0], 0.f)); ha[m][1] = tf32r(fmaxf(hc[m][2], 0.f));
+                ha[m][2] = tf32r(fmaxf(hc[m][1], 0.f)); ha[m][3] = tf32r(fmaxf(hc[m][3], 0.f));
+            }
             const float* w2p = W2s + g * P2 + 8 * c + 2 * t;
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
                 const float2 w = *reinterpret_cast<const float2*>(w2p + 8 * nt * P2);
-                mma_tf32(o[nt], ha, w.x, w.y);
+#pragma unroll
+                for (int m = 0; m < MT; ++m) mma_tf32(o[m][nt], ha[m], w.x, w.y);
             }
         }
         // z = acc + b2 + x1 (exact fp32 residual, re-read: the block's rows are L1-resident), then LayerNorm over E
-        float s_lo = 0.f, s_hi = 0.f;
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            const int col = 8 * nt + 2 * t;
-            const float2 rl = v_lo ? __ldg(reinterpret_cast<const float2*>(x_lo + col)) : make_float2(0.f, 0.f);
-            const float2 rh = v_hi ? __ldg(reinterpret_cast<const float2*>(x_hi + col)) : make_float2(0.f, 0.f);
-            o[nt][0] += b2s[col] + rl.x; o[nt][1] += b2s[col + 1] + rl.y;
-            o[nt][2] += b2s[col] + rh.x; o[nt][3] += b2s[col + 1] + rh.y;
-            s_lo += o[nt][0] + o[nt][1]; s_hi += o[nt][2] + o[nt][3];
-        }
-        const float m_lo = quad_sum(s_lo) * inv_e, m_hi = quad_sum(s_hi) * inv_e;
-        float q_lo = 0.f, q_hi = 0.f;
+        for (int m = 0; m < MT; ++m) {
+            const int r_lo = blk * RPB + 16 * m + g, r_hi = r_lo + 8;
+            const bool v_lo = r_lo < rows, v_hi = r_hi < rows;
+            const float* x_lo = a.X + (size_t)r_lo * E;
+            const float* x_hi = a.X + (size_t)r_hi * E;
+            float s_lo = 0.f, s_hi = 0.f;
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            o[nt][0] -= m_lo; o[nt][1] -= m_lo; o[nt][2] -= m_hi; o[nt][3] -= m_hi;
-            q_lo = fmaf(o[nt][0], o[nt][0], fmaf(o[nt][1], o[nt][1], q_lo));
-            q_hi = fmaf(o[nt][2], o[nt][2], fmaf(o[nt][3], o[nt][3], q_hi));
-        }
-        const float rs_lo = rsqrtf(quad_sum(q_lo) * inv_e + a.eps), rs_hi = rsqrtf(quad_sum(q_hi) * inv_e + a.eps);
-        if (a.rstd && t == 0) {
-            if (v_lo) a.rstd[r_lo] = rs_lo;
-            if (v_hi) a.rstd[r_hi] = rs_hi;
-        }
-        uint32_t rk_lo = 0, rk_hi = 0;
-        if (a.drop.thresh) { rk_lo = drop_rowkey(a.drop, (uint32_t)r_lo); rk_hi = drop_rowkey(a.drop, (uint32_t)r_hi); }
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            const int col = 8 * nt + 2 * t;
-            const float h0 = o[nt][0] * rs_lo, h1 = o[nt][1] * rs_lo, h2 = o[nt][2] * rs_hi, h3 = o[nt][3] * rs_hi;
-            float y0 = fmaf(h0, gs[col], bs[col]), y1 = fmaf(h1, gs[col + 1], bs[col + 1]);
-            float y2 = fmaf(h2, gs[col], bs[col]), y3 = fmaf(h3, gs[col + 1], bs[col + 1]);
-            if (a.drop.thresh) {
-                y0 *= drop_scale(a.drop, rk_lo, (uint32_t)col); y1 *= drop_scale(a.drop, rk_lo, (uint32_t)col + 1);
-                y2 *= drop_scale(a.drop, rk_hi, (uint32_t)col); y3 *= drop_scale(a.drop, rk_hi, (uint32_t)col + 1);
+            for (int nt = 0; nt < NT; ++nt) {
+                const int col = 8 * nt + 2 * t;
+                const float2 rl = v_lo ? __ldg(reinterpret_cast<const float2*>(x_lo + col)) : make_float2(0.f, 0.f);
+                const float2 rh = v_hi ? __ldg(reinterpret_cast<const float2*>(x_hi + col)) : make_float2(0.f, 0.f);
+                o[m][nt][0] += b2s[col] + rl.x; o[m][nt][1] += b2s[col + 1] + rl.y;
+                o[m][nt][2] += b2s[col] + rh.x; o[m][nt][3] += b2s[col + 1] + rh.y;
+                s_lo += o[m][nt][0] + o[m][nt][1]; s_hi += o[m][nt][2] + o[m][nt][3];
             }
-            if (v_lo) {
-                *reinterpret_cast<float2*>(a.Y + (size_t)r_lo * E + col) = make_float2(y0, y1);
-                if (a.xhat) *reinterpret_cast<float2*>(a.xhat + (size_t)r_lo * E + col) = make_float2(h0, h1);
+            const float m_lo = quad_sum(s_lo) * inv_e, m_hi = quad_sum(s_hi) * inv_e;
+            float q_lo = 0.f, q_hi = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                o[m][nt][0] -= m_lo; o[m][nt][1] -= m_lo; o[m][nt][2] -= m_hi; o[m][nt][3] -= m_hi;
+                q_lo = fmaf(o[m][nt][0], o[m][nt][0], fmaf(o[m][nt][1], o[m][nt][1], q_lo));
+                q_hi = fmaf(o[m][nt][2], o[m][nt][2], fmaf(o[m][nt][3], o[m][nt][3], q_hi));
             }
-            if (v_hi) {
-                *reinterpret_cast<float2*>(a.Y + (size_t)r_hi * E + col) = make_float2(y2, y3);
-                if (a.xhat) *reinterpret_cast<float2*>(a.xhat + (size_t)r_hi * E + col) = make_float2(h2, h3);
+            const float rs_lo = rsqrtf(quad_sum(q_lo) * inv_e + a.eps), rs_hi = rsqrtf(quad_sum(q_hi) * inv_e + a.eps);
+            if (a.rstd && t == 0) {
+                if (v_lo) a.rstd[r_lo] = rs_lo;
+                if (v_hi) a.rstd[r_hi] = rs_hi;
+            }
+            uint32_t rk_lo = 0, rk_hi = 0;
+            if (a.drop.thresh) { rk_lo = drop_rowkey(a.drop, (uint32_t)r_lo); rk_hi = drop_rowkey(a.drop, (uint32_t)r_hi); }
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const int col = 8 * nt + 2 * t;
+                const float h0 = o[m][nt][0] * rs_lo, h1 = o[m][nt][1] * rs_lo, h2 = o[m][nt][2] * rs_hi, h3 = o[m][nt][3] * rs_hi;
+                float y0 = fmaf(h0, gs[col], bs[col]), y1 = fmaf(h1, gs[col + 1], bs[col + 1]);
+                float y2 = fmaf(h2, gs[col], bs[col]), y3 = fmaf(h3, gs[col + 1], bs[col + 1]);
+                if (a.drop.thresh) {
+                    y0 *= drop_scale(a.drop, rk_lo, (uint32_t)col); y1 *= drop_scale(a.drop, rk_lo, (uint32_t)col + 1);
+                    y2 *= drop_scale(a.drop, rk_hi, (uint32_t)col); y3 *= drop_scale(a.drop, rk_hi, (uint32_t)col + 1);
+                }
+                if (v_lo) {
+                    *reinterpret_cast<float2*>(a.Y + (size_t)r_lo * E + col) = make_float2(y0, y1);
+                    if (a.xhat) *reinterpret_cast<float2*>(a.xhat + (size_t)r_lo * E + col) = make_float2(h0, h1);
+                }
+                if (v_hi) {
+                    *reinterpret_cast<float2*>(a.Y + (size_t)r_hi * E + col) = make_float2(y2, y3);
+                    if (a.xhat) *reinterpret_cast<float2*>(a.xhat + (size_t)r_hi * E + col) = make_float2(h2, h3);
+                }
             }
         }
     }
@@ -229,7 +258,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_bwd_kernel(const FfnBwdArgs
     float* hs = x1s + TT * PX;
     float* dhs = hs + TT * PH;
     pdl_trigger();
-    stage_weights<E>(W1s, W2s, vec, a.W1, a.b1, a.W2, nullptr, a.gamma, nullptr);
+    stage_weights<E, FF_THREADS>(W1s, W2s, vec, a.W1, a.b1, a.W2, nullptr, a.gamma, nullptr);
     __syncthreads();
     pdl_wait();
     const int rows = a.n_rows_dev ? min(__ldg(a.n_rows_dev), a.M_cap) : a.M_cap;
@@ -397,22 +426,22 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_bwd_kernel(const FfnBwdArgs
     }
 }
 
-template <int E>
+template <int E, int MT, int WARPS>
 int launch_fwd_t(const FfnFwdArgs& a, cudaStream_t st) {
     using G = FfnGeom<E>;
     static bool configured = false;
     if (!configured) {
-        MVN_CUDA(cudaFuncSetAttribute(ffn_fwd_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_FWD));
+        MVN_CUDA(cudaFuncSetAttribute(ffn_fwd_kernel<E, MT, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_FWD));
         configured = true;
     }
-    const int blocks = cdiv(a.M_cap, 16 * FF_WARPS);
+    const int blocks = cdiv(a.M_cap, 16 * MT * WARPS);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(blocks < num_sms() ? blocks : num_sms()); cfg.blockDim = dim3(FF_THREADS); cfg.dynamicSmemBytes = G::SMEM_FWD; cfg.stream = st;
+    cfg.gridDim = dim3(blocks < num_sms() ? blocks : num_sms()); cfg.blockDim = dim3(WARPS * 32); cfg.dynamicSmemBytes = G::SMEM_FWD; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    MVN_CUDA(cudaLaunchKernelEx(&cfg, ffn_fwd_kernel<E>, a));
+    MVN_CUDA(cudaLaunchKernelEx(&cfg, ffn_fwd_kernel<E, MT, WARPS>, a));
     MVN_LAUNCH_CHECK();
     return 0;
 }
@@ -450,7 +479,9 @@ int launch_ffn_fused_fwd(const float* X, const float* W1, const float* b1, const
     FfnFwdArgs a;
     a.X = X; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2; a.gamma = gamma; a.beta = beta; a.Y = Y; a.xhat = xhat; a.rstd = rstd;
     a.n_rows_dev = n_rows_dev; a.M_cap = M_cap; a.eps = eps; a.drop = drop;
-    return E == 64 ? launch_fwd_t<64>(a, st) : launch_fwd_t<32>(a, st);
+    static const int variant = getenv("MVN_FFN_FWD") ? atoi(getenv("MVN_FFN_FWD")) : 1;      // 0: one 16-row tile per warp (A/B measurements)
+    if (variant == 0) return E == 64 ? launch_fwd_t<64, 1, 16>(a, st) : launch_fwd_t<32, 1, 16>(a, st);
+    return E == 64 ? launch_fwd_t<64, 2, 8>(a, st) : launch_fwd_t<32, 2, 16>(a, st);
 }
 
 int launch_ffn_fused_bwd(const float* dY, const float* xhat, const float* rstd, const float* X, const float* W1, const float* b1,

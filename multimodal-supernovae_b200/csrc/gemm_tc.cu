@@ -14,6 +14,8 @@
 //   * warps 2-5: epilogue -- tcgen05.ld gives every thread one output row (32 columns at a time), so LayerNorm
 //     statistics need no shuffles; tiles go through a small per-warp shared-memory transpose so that every global
 //     load/store of C, the residual, xhat ... is a full 128-byte line (TMA loads in, TMA stores out).
+#include <stdlib.h>
+
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -115,6 +117,7 @@ struct TcArgs {
     const int32_t* n_rows_dev;
     int M_cap, N, K, b_is_nk;
     int nA, nX;                  // ring split; nX == 0: no aux tile
+    float wscale;                // weights are staged as tf32(W * wscale): see trunc_comp()
     GemmEpilogue ep;
 };
 
@@ -202,14 +205,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
                 if (a.b_is_nk) {         // B[n][k], k contiguous: 4 consecutive k of one row n -> one 16-byte chunk
                     const int n = i / (K >> 2), k = (i % (K >> 2)) << 2;
                     *reinterpret_cast<float4*>(Bs + (size_t)(k >> 5) * N * 32 + sw128_off(n, k & 31)) =
-                        make_float4(to_tf32(w[u].x), to_tf32(w[u].y), to_tf32(w[u].z), to_tf32(w[u].w));
+                        make_float4(to_tf32(w[u].x * a.wscale), to_tf32(w[u].y * a.wscale), to_tf32(w[u].z * a.wscale), to_tf32(w[u].w * a.wscale));
                 } else {                 // B[k][n], n contiguous: transpose while staging (4 rows n of one column k)
                     const int k = i / (N >> 2), n = (i % (N >> 2)) << 2;
                     float* dst = Bs + (size_t)(k >> 5) * N * 32;
-                    dst[sw128_off(n, k & 31)] = to_tf32(w[u].x);
-                    dst[sw128_off(n + 1, k & 31)] = to_tf32(w[u].y);
-                    dst[sw128_off(n + 2, k & 31)] = to_tf32(w[u].z);
-                    dst[sw128_off(n + 3, k & 31)] = to_tf32(w[u].w);
+                    dst[sw128_off(n, k & 31)] = to_tf32(w[u].x * a.wscale);
+                    dst[sw128_off(n + 1, k & 31)] = to_tf32(w[u].y * a.wscale);
+                    dst[sw128_off(n + 2, k & 31)] = to_tf32(w[u].z * a.wscale);
+                    dst[sw128_off(n + 3, k & 31)] = to_tf32(w[u].w * a.wscale);
                 }
             }
         }
@@ -621,6 +624,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const __grid_co
 
 }  // namespace
 
+// The tensor core TRUNCATES the fp32 bit patterns TMA hands it as the A operand to TF32 (the low 13 mantissa bits are ignored),
+// which shrinks every activation by eps in [0, 2^-10) of itself: a bias of E[eps] = 2^-11 * E[1/mantissa] ~ 3.5e-4 on every
+// output, the same sign in every layer.  The weights are staged by this kernel anyway, so they carry the compensation
+// (1 + E[eps]) and are then rounded to nearest: what remains of the truncation is zero-mean.  MVN_TRUNC_COMP overrides (0 = off).
+static float trunc_comp() {
+    static float v = -1.f;
+    if (v < 0.f) {
+        const char* e = getenv("MVN_TRUNC_COMP");
+        v = e ? 1.0f + (float)atof(e) : 1.0f + 3.52e-4f;
+    }
+    return v;
+}
+
 int launch_gemm_tc(const float* A, const float* Bm, float* C, const int32_t* n_rows_dev, int M_cap, int N, int K, bool b_is_nk,
                    const GemmEpilogue& ep, cudaStream_t st) {
     // shapes this kernel is built for; anything else stays on the FFMA kernel
@@ -640,6 +656,7 @@ int launch_gemm_tc(const float* A, const float* Bm, float* C, const int32_t* n_r
     TcArgs a;
     a.B = Bm; a.C = C; a.n_rows_dev = n_rows_dev; a.M_cap = M_cap; a.N = N; a.K = K; a.b_is_nk = b_is_nk ? 1 : 0; a.ep = ep;
     a.nA = NSTAGE; a.nX = 0;
+    a.wscale = trunc_comp();
     if (aux) {
         tx = get_tmap_2d(aux, M_cap, N, TILE_M, false);
         if (!tx) return MVN_E_BADARG;

@@ -206,6 +206,31 @@ extern "C" int mvn_mse_bwd(const float* pred, const float* target, int n, const 
     MVN_LAUNCH_CHECK();
     return 0;
 }
+// retrieval curve: counts[t] = #{j : rank_j < k_thr[t]}  (get_ROC_data's "idx in idx_sorted[:int(threshold * N)]" summed over sources)
+__global__ void __launch_bounds__(256) rank_curve_kernel(const int32_t* __restrict__ ranks, int N, const int32_t* __restrict__ k_thr, int n_thr,
+                                                         int32_t* __restrict__ counts) {
+    extern __shared__ int32_t sk[];          // thresholds | per-CTA counts
+    int32_t* sc = sk + n_thr;
+    for (int i = threadIdx.x; i < n_thr; i += blockDim.x) { sk[i] = k_thr[i]; sc[i] = 0; }
+    __syncthreads();
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+        const int r = ranks[j];
+        for (int t = 0; t < n_thr; ++t)
+            if (r < sk[t]) atomicAdd(&sc[t], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_thr; i += blockDim.x)
+        if (sc[i]) atomicAdd(&counts[i], sc[i]);      // integer atomics: order-independent, deterministic
+}
+extern "C" int mvn_retrieval_curve(const int32_t* ranks, int N, const int32_t* k_thr, int n_thr, int32_t* counts, void* stream) {
+    MVN_CHECK_ARG(ranks && k_thr && counts && N > 0 && n_thr > 0 && n_thr <= 4096, "retrieval_curve: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    MVN_CUDA(cudaMemsetAsync(counts, 0, (size_t)n_thr * sizeof(int32_t), st));
+    const int grid = cdiv(N, 256) < 4 * num_sms() ? cdiv(N, 256) : 4 * num_sms();
+    rank_curve_kernel<<<grid, 256, 2 * (size_t)n_thr * sizeof(int32_t), st>>>(ranks, N, k_thr, n_thr, counts);
+    MVN_LAUNCH_CHECK();
+    return 0;
+}
 extern "C" int mvn_retrieval_ranks(const float* e1, const float* e2, int N, int D, int32_t* ranks, void* stream) {
     MVN_CHECK_ARG(e1 && e2 && ranks && N > 0 && D > 0 && D <= 8192, "retrieval_ranks: bad arguments");
     ranks_kernel<<<N, 256, D * sizeof(float), (cudaStream_t)stream>>>(e1, e2, N, D, ranks);

@@ -166,6 +166,9 @@ class LightCurveImageCLIP(_Base):
             self.class_emb = nn.Embedding(n_classes, self.len_meta_input // 2)
             self.meta_encoder = MLP(output_dim=enc_dim, **meta_kwargs)
         self.loss = loss
+        if loss != "softmax" and not (regression or classification):
+            raise NotImplementedError(f"maven_b200 builds the softmax CLIP loss only (every reference driver sets loss='softmax'); got loss={loss!r}. "
+                                      "Keep the reference module for the SigLIP variant.")
         self.linear_out = 1
         if self.classification:
             self.linear_out = self.n_classes
@@ -257,7 +260,9 @@ class LightCurveImageCLIP(_Base):
 
     def _new_gbuf(self, g: ops.FlatParams, device):
         if torch.is_grad_enabled():
-            self._gbuf = torch.empty(g.total, dtype=torch.float32, device=device)
+            # zeros, not empty: slots of parameters that receive no gradient this step (logit_scale of a classifier, a frozen
+            # backbone) are part of what the data-parallel all-reduce and any norm / clipping over the flat buffer read
+            self._gbuf = torch.zeros(g.total, dtype=torch.float32, device=device)
         else:
             self._gbuf = None
         return self._gbuf
@@ -364,7 +369,7 @@ class LightCurveImageCLIP(_Base):
         if self.regression:
             if self.track_predictions:
                 self.y_pred.append(x.flatten()); self.y_true.append(redshift)
-            return ops.MSEFn.apply(x.squeeze(), redshift)
+            return ops.dp_weighted_mean(ops.MSEFn.apply(x.squeeze(), redshift), float(redshift.numel()))
         if self.classification:
             if self.n_classes == 5:
                 w = [0.3, 0.08, 1.0, 0.01, 0.2]
@@ -378,7 +383,8 @@ class LightCurveImageCLIP(_Base):
                 self._class_w = cw
             if self.track_predictions:
                 self.y_pred.append(x); self.y_true.append(classification)
-            return ops.WeightedCEFn.apply(x.squeeze(), classification, cw)
+            loss, wsum = ops.WeightedCEFn.apply(x.squeeze(), classification, cw)
+            return ops.dp_weighted_mean(loss, wsum)
         if self.loss == "softmax":
             return clip_loss_multimodal(x, self.logit_scale, self.logit_bias, prec=0)   # 0-dim already: .mean() is the identity
         raise NotImplementedError("maven_b200 builds the softmax CLIP loss only (every reference driver sets loss='softmax')")
@@ -387,3 +393,43 @@ class LightCurveImageCLIP(_Base):
         loss = self.training_loss(batch)
         self.log("train_loss", loss, on_epoch=True, on_step=False, prog_bar=True, logger=True)
         return loss
+
+    # ---- validation, CLIP branch (src/models_multimodal.py:418-553): collect the embeddings, log the retrieval AUC of every
+    # modality pair at epoch end.  The reference's O(N^2) Python loop is two kernels here (maven_b200.utils.get_AUC).
+    def on_validation_start(self) -> None:
+        self.embs_list = [[] for _ in range(len(self.combinations))]
+        if self.regression or self.classification:
+            self.y_pred_val, self.y_true_val = [], []
+
+    def validation_step(self, batch, batch_idx):
+        x_img, x_lc, t_lc, mask_lc, x_sp, t_sp, mask_sp, redshift, classification = batch
+        if self.regression or self.classification:
+            track, self.track_predictions = self.track_predictions, False
+            try:
+                with torch.no_grad():
+                    loss = self.training_loss(batch)
+            finally:
+                self.track_predictions = track
+        else:
+            with torch.no_grad():
+                x = self(x_img, x_lc, t_lc, mask_lc, x_sp, t_sp, mask_sp, redshift, classification)
+                for i in range(len(self.embs_list)):
+                    self.embs_list[i].append(x[i])
+                loss = clip_loss_multimodal(x, self.logit_scale, self.logit_bias, prec=0)
+        self.log("val_loss", loss, on_epoch=True, on_step=False, prog_bar=True, logger=True)
+        return loss
+
+    def on_validation_epoch_end(self) -> None:
+        if self.regression or self.classification or not getattr(self, "embs_list", None):
+            return
+        from .utils import get_AUC
+        embs = [torch.cat(e, dim=0) for e in self.embs_list]
+        if len(self.combinations) == 2:
+            self.log("AUC_val", get_AUC(embs[0], embs[1]), on_epoch=True, on_step=False, prog_bar=True, logger=True)
+        else:
+            count = 1
+            for i in range(len(self.combinations) - 1):
+                for j in range(i + 1, len(self.combinations)):
+                    self.log(f"AUC_val{count}", get_AUC(embs[i], embs[j]), on_epoch=True, on_step=False, prog_bar=True, logger=True)
+                    count += 1
+        self.embs_list = None

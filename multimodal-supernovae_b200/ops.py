@@ -702,10 +702,12 @@ class WeightedCEFn(torch.autograd.Function):
         check(L.mvn_weighted_ce_fwd(_p(logits), _p(labels), _p(class_w), B, C, _p(buf), _stream()), "weighted_ce_fwd")
         _count(2)
         ctx.save_for_backward(logits, labels, class_w, buf)
-        return buf[0].clone().reshape(())
+        wsum = buf[1].clone().reshape(())                      # sum of the class weights of this batch (the loss's denominator)
+        ctx.mark_non_differentiable(wsum)
+        return buf[0].clone().reshape(()), wsum
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, _gw=None):
         L = lib()
         logits, labels, class_w, buf = ctx.saved_tensors
         B, C = logits.shape
@@ -740,6 +742,37 @@ class MSEFn(torch.autograd.Function):
         return d, None
 
 
+class _DPWeightedMeanFn(torch.autograd.Function):
+    """Global-batch value of a per-rank weighted mean: sum_r(loss_r * w_r) / sum_r(w_r).  Backward scales the local
+    gradient by w_local / w_global, so that the SUM all-reduce of the flat gradient buffer yields the gradient of the
+    global-batch loss (a plain local mean would come out world-size times too large, and for the weighted cross-entropy
+    normalised by the wrong denominator)."""
+
+    @staticmethod
+    def forward(ctx, loss_local, w_local, group):
+        import torch.distributed as dist
+        pair = torch.stack([loss_local.reshape(()) * w_local.reshape(()), w_local.reshape(())])
+        dist.all_reduce(pair, group=group)
+        ctx.save_for_backward(w_local.reshape(()) / pair[1])
+        return pair[0] / pair[1]
+
+    @staticmethod
+    def backward(ctx, g):
+        (ratio,) = ctx.saved_tensors
+        return g * ratio, None, None
+
+
+def dp_weighted_mean(loss_local: torch.Tensor, weight_local) -> torch.Tensor:
+    """MSE / weighted-CE heads under data parallelism (src/models_multimodal.py:326,335-349 define them on the whole batch):
+    identity on one process; with a data-parallel group the global-batch loss with the matching gradient scale."""
+    grp = _DP_GROUP
+    if grp is None:
+        return loss_local
+    if not torch.is_tensor(weight_local):
+        weight_local = torch.full((), float(weight_local), dtype=loss_local.dtype, device=loss_local.device)   # a fill kernel: graph-capturable
+    return _DPWeightedMeanFn.apply(loss_local, weight_local.to(loss_local.dtype), grp)
+
+
 def retrieval_ranks(e1: torch.Tensor, e2: torch.Tensor) -> torch.Tensor:
     L = lib()
     e1 = _req(e1, "embs1"); e2 = _req(e2, "embs2")
@@ -748,3 +781,13 @@ def retrieval_ranks(e1: torch.Tensor, e2: torch.Tensor) -> torch.Tensor:
     check(L.mvn_retrieval_ranks(_p(e1), _p(e2), N, D, _p(r), _stream()), "retrieval_ranks")
     _count(1)
     return r
+
+
+def retrieval_curve(ranks: torch.Tensor, k_thr: torch.Tensor) -> torch.Tensor:
+    """counts[t] = #{j : ranks[j] < k_thr[t]} (mvn_retrieval_curve); both int32 CUDA tensors."""
+    L = lib()
+    ranks = _req(ranks, "ranks", torch.int32); k_thr = _req(k_thr, "k_thr", torch.int32)
+    counts = torch.empty(k_thr.numel(), dtype=torch.int32, device=ranks.device)
+    check(L.mvn_retrieval_curve(_p(ranks), ranks.numel(), _p(k_thr), k_thr.numel(), _p(counts), _stream()), "retrieval_curve")
+    _count(1)
+    return counts

@@ -67,6 +67,51 @@ class FusedRAdam(torch.optim.Optimizer):
             stepped = getattr(self, "_stepped", None)
             self._steps = [s + 1 if (stepped is None or stepped[k]) else s for k, s in enumerate(self._steps)]
 
+    # ---- checkpoint format: torch.optim.RAdam's ------------------------------------------------------------------
+    # The moments live in two flat buffers, not in Optimizer.state; state_dict() / load_state_dict() translate to and from
+    # torch.optim.RAdam's per-parameter {'step', 'exp_avg', 'exp_avg_sq'} entries, so Lightning checkpoints written through
+    # configure_optimizers() resume exactly and a reference RAdam state loads into this optimizer (and vice versa).
+    def state_dict(self):
+        g: ops.FlatParams = self.model.flat_group()
+        self.state.clear()
+        if self._m is not None:
+            if getattr(self, "_step_dev", None) is not None:          # device-side stepping: the device counter is the truth
+                n = int(self._step_dev.item())
+                stepped = getattr(self, "_stepped", None)
+                steps = [n if (stepped is None or stepped[k]) else s_ for k, s_ in enumerate(self._steps)]
+            else:
+                steps = self._steps
+            for k, p in enumerate(g.params):
+                if steps[k] == 0:
+                    continue                                          # torch creates state lazily, at a parameter's first step
+                o, n_ = g.offsets[k], g.sizes[k]
+                self.state[p] = {"step": torch.tensor(float(steps[k]), dtype=torch.float32),
+                                 "exp_avg": self._m[o:o + n_].view(p.shape).clone(),
+                                 "exp_avg_sq": self._v[o:o + n_].view(p.shape).clone()}
+        try:
+            return super().state_dict()
+        finally:
+            self.state.clear()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)                           # validates the groups, maps ids -> parameters, casts to device
+        g: ops.FlatParams = self.model.flat_group()
+        flat = g.ensure()
+        self._m = self._v = None
+        self._ensure_state(g, flat)
+        index = {id(p): k for k, p in enumerate(g.params)}
+        for p, st in list(self.state.items()):
+            k = index.get(id(p))
+            if k is None:
+                continue
+            o, n_ = g.offsets[k], g.sizes[k]
+            self._m[o:o + n_].copy_(st["exp_avg"].reshape(-1))
+            self._v[o:o + n_].copy_(st["exp_avg_sq"].reshape(-1))
+            self._steps[k] = int(round(float(st["step"])))
+        self.state.clear()
+        if getattr(self, "_step_dev", None) is not None:
+            self._step_dev.fill_(max(self._steps) if self._steps else 0)
+
     def _ensure_state(self, g: ops.FlatParams, flat: torch.Tensor):
         if self._m is None or self._m.numel() != g.total or self._m.device != flat.device:
             self._m = torch.zeros_like(flat)

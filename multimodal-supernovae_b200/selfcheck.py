@@ -44,14 +44,28 @@ def run_smoke():
     batch = (None, x_lc, t_lc, m_lc, x_sp, t_sp, m_sp, None, None)
     cfg = dict(combinations=["lightcurve", "spectral"], nband=2, transformer_kwargs=tk, transformer_spectral_kwargs=sk)
     ref = O.training_loss(sd, cfg, batch).item()
-    model.to(dev).train()
     gb = tuple(None if v is None else v.to(dev) for v in batch)
-    opt = model.configure_optimizers()["optimizer"]
-    loss = model.training_step(gb, 0)
-    loss.backward()
-    opt.step()
-    torch.cuda.synchronize()
-    got = loss.item()
-    rel = abs(got - ref) / abs(ref)
-    print(f"smoke: loss gpu={got:.7f} oracle={ref:.7f} rel={rel:.2e}")
-    assert rel < 1e-5, "CUDA training step disagrees with the CPU oracle"
+    from maven_b200 import _lib
+    from maven_b200.transformer_utils import set_precision
+    L = _lib.lib()
+    # the tier the benchmark runs: tcgen05 GEMMs + warp-MMA attention + fused feed-forward kernels, 1e-3 bar (north_star);
+    # the tier counters prove that those kernels -- not the FFMA ones -- executed the encoder layers
+    for tier, tol in (("fp32", 1e-5), ("fused", 1e-3)):
+        torch.manual_seed(0)
+        m = LightCurveImageCLIP(logit_scale=19.55, nband=2, loss="softmax", transformer_kwargs=tk, transformer_spectral_kwargs=sk,
+                                combinations=["lightcurve", "spectral"], lr=1e-3, optimizer_kwargs={"weight_decay": 5.6e-4})
+        m.load_state_dict(sd)
+        set_precision(m.to(dev).train(), tier)
+        opt = m.configure_optimizers()["optimizer"]
+        L.mvn_tier_reset()
+        loss = m.training_step(gb, 0)
+        loss.backward()
+        opt.step()
+        torch.cuda.synchronize()
+        got = loss.item()
+        rel = abs(got - ref) / abs(ref)
+        tiers = [L.mvn_tier_count(i) for i in range(4)]
+        print(f"smoke[{tier}]: loss gpu={got:.7f} oracle={ref:.7f} rel={rel:.2e} launches by tier (ffma, tcgen05, mma attention, fused)={tiers}")
+        assert rel < tol, f"CUDA training step ({tier}) disagrees with the CPU oracle"
+        if tier == "fused":
+            assert tiers[1] > 0 and tiers[2] == 8 and tiers[3] == 8, "tensor-core / fused kernels did not run"

@@ -349,6 +349,25 @@ def retrieval_ranks(e1: Tensor, e2: Tensor) -> Tensor:
     return (sim > sim.diag()[None, :]).sum(dim=0)
 
 
+def roc_data(e1: Tensor, e2: Tensor, n_thr: int = 100):
+    """get_ROC_data (src/utils.py:380-413): thresholds = linspace(0,1,100); source j is "right" at threshold t when its true
+    partner is among the first int(t*N) entries of its descending similarity ranking, i.e. rank_j < int(t*N).
+    -> (thresholds float64 [n_thr], fraction_correct float64 [n_thr])."""
+    import numpy as np
+    N = e1.shape[0]
+    thresholds = np.linspace(0, 1, n_thr)
+    ranks = retrieval_ranks(e1, e2).numpy()
+    k = np.array([int(t * N) for t in thresholds])
+    return thresholds, (ranks[None, :] < k[:, None]).sum(axis=1) / N
+
+
+def auc(e1: Tensor, e2: Tensor) -> float:
+    """get_AUC (src/utils.py:416-426): trapezoid area under the curve above."""
+    import numpy as np
+    thr, frac = roc_data(e1, e2)
+    return float(np.sum((frac[1:] + frac[:-1]) * np.diff(thr)) / 2.0)
+
+
 # --------------------------------------------------------------------------------------
 # N1  NoisyDataLoader.__iter__ on GIVEN random tensors             src/dataloader.py:88-287
 # (the reference draws rand_like(images), randn_like(mag), randn_like(spec), randint(0,4) from

@@ -18,40 +18,12 @@ REF = os.environ.get("MAVEN_REFERENCE", "/root/reference")
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _stub_modules():
-    def mod(name, **attrs):
-        m = types.ModuleType(name)
-        for k, v in attrs.items():
-            setattr(m, k, v)
-        sys.modules[name] = m
-        return m
-
-    class _LM(nn.Module):
-        def log(self, *a, **k):
-            pass
-
-    mod("pytorch_lightning", LightningModule=_LM, Callback=object, Trainer=object)
-    mod("pytorch_lightning.callbacks", Callback=object)
-    mod("ruamel"); mod("ruamel.yaml", YAML=object)
-    mod("torchmetrics"); mod("torchmetrics.classification", MulticlassFBetaScore=object)
-    mp = mod("matplotlib"); mod("matplotlib.pyplot"); mod("matplotlib.ticker", MaxNLocator=object)
-    mp.pyplot = sys.modules["matplotlib.pyplot"]
-    mp.ticker = sys.modules["matplotlib.ticker"]
-    mod("seaborn")
-    if "wandb" not in sys.modules:
-        try:
-            import wandb  # noqa: F401
-        except Exception:
-            mod("wandb")
-
-
 def import_reference():
-    _stub_modules()
-    sys.path.insert(0, REF)
-    from src import loss as rloss
-    from src import transformer_utils as rtu
-    from src import models_multimodal as rmm
-    return rtu, rloss, rmm
+    """The unmodified reference modules, framework imports stubbed (oracle/ref_loader.py)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import ref_loader
+    os.environ.setdefault("MAVEN_REFERENCE", REF)
+    return ref_loader.import_reference()
 
 
 def ragged_seq(gen, B, T, nband, tmax, lo=1):

@@ -1,0 +1,116 @@
+"""Full-model parity in the tiers the benchmark runs (tf32, fused): loss and the 128-d embeddings of
+LightCurveImageCLIP.training_step at the real C4 / C3 / C5 configurations (full depth) against the fp32 CPU oracle,
+north_star's reduced-precision bar 1e-3 -- the benchmarked number is only valid if THIS passes.  Plus: the streamed CLIP
+loss at the large global batches of config C5 (fp64 reference on a row subset), and data-parallel parity on real GPUs
+whenever more than one is visible."""
+import math
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL_REDUCED = 1e-3
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("workload", ["c4", "c3", "c5", "c2"])
+@pytest.mark.parametrize("tier", ["tf32", "fused"])
+def test_training_step_reduced_precision_vs_oracle(workload, tier):
+    import bench
+    from maven_b200 import _lib
+    from maven_b200.models_multimodal import LightCurveImageCLIP
+    from maven_b200.transformer_utils import set_precision
+    from oracle import maven_oracle as O
+    L = _lib.lib()
+    wl = bench.WORKLOADS[workload]
+    B = 64
+    batch = bench.make_batch(wl, B, seed=99)
+    torch.manual_seed(0)
+    model = LightCurveImageCLIP(**bench.model_kwargs(wl, 0.0))
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    cfg = dict(combinations=wl["combinations"], nband=2, transformer_kwargs=wl["lc"], transformer_spectral_kwargs=wl["sp"],
+               classification=wl.get("classification", False), n_classes=wl.get("n_classes", 5), conv_kwargs=bench.CONV)
+    with torch.no_grad():
+        ref_out = O.model_forward(sd, cfg, batch, training=True)
+        ref_loss = O.training_loss(sd, cfg, batch).item()
+    model = set_precision(model.to(dev()).train(), tier)
+    gb = [None if v is None else v.to(dev()) for v in batch]
+    L.mvn_tier_reset()
+    with torch.no_grad():
+        out = model(*gb)
+    loss = model.training_step(gb, 0)
+    loss.backward()
+    torch.cuda.synchronize()
+    # the tensor-core kernels ran (nothing fell back to FFMA for the encoder layers) and, in the fused tier, the fused ones did
+    depth_total = wl["lc"]["depth"] + (wl["sp"]["depth"] if wl["sp"] else 0)
+    assert L.mvn_tier_count(1) > 0 and L.mvn_tier_count(2) == 3 * depth_total       # tcgen05 GEMMs; warp-MMA attention: 2 fwd + 1 bwd per layer
+    if tier == "fused":
+        assert L.mvn_tier_count(3) >= 3 * depth_total                               # 2 forwards (no_grad + training) + 1 backward per layer
+    outs = out if isinstance(out, list) else [out]
+    refs = ref_out if isinstance(ref_out, list) else [ref_out]
+    errs = [relerr(o, r) for o, r in zip(outs, refs)]
+    el = abs(loss.item() - ref_loss) / abs(ref_loss)
+    print(f"{workload} {tier}: loss rel {el:.2e}, embedding relerr {['%.2e' % e for e in errs]}")
+    assert el < TOL_REDUCED
+    assert max(errs) < (TOL_REDUCED if not wl.get("classification") else 2e-3), errs      # logits of the classifier head: un-normalised 5-vector
+    assert all(p.grad is None or torch.isfinite(p.grad).all() for p in model.parameters())
+
+
+@pytest.mark.parametrize("N", [8192, 65536])
+def test_clip_loss_large_global_batch(N):
+    """N x N never materialised: loss + gradients of the streamed kernels at the global batches of config C5 against an fp64
+    reference that needs only O(N) memory per row block (LSE over column blocks)."""
+    from maven_b200.loss import clip_loss
+    gen = torch.Generator().manual_seed(N)
+    D = 128
+    e1 = torch.nn.functional.normalize(torch.randn(N, D, generator=gen), dim=-1)
+    e2 = torch.nn.functional.normalize(torch.randn(N, D, generator=gen) + 0.5 * e1 * math.sqrt(D), dim=-1)   # correlated pairs: a trained-like diagonal
+    ls, lb = torch.tensor(math.log(19.55)), torch.tensor(-10.0)
+    e1c, e2c = e1.to(dev()).requires_grad_(), e2.to(dev()).requires_grad_()
+    lsc, lbc = ls.to(dev()).requires_grad_(), lb.to(dev()).requires_grad_()
+    loss = clip_loss(e1c, e2c, lsc, lbc)
+    g1, g2, gls, _ = torch.autograd.grad(loss, [e1c, e2c, lsc, lbc])
+    # fp64 reference on the GPU, blocked: Z = s * e2 e1^T + b  (rows: e2, columns: e1)
+    s = math.exp(ls.item())
+    a, b = e2.to(dev()).double(), e1.to(dev()).double()
+    blk = 2048
+    lse_r = torch.cat([torch.logsumexp(s * a[i:i + blk] @ b.t() + lb.item(), dim=1) for i in range(0, N, blk)])
+    lse_c = torch.cat([torch.logsumexp(s * b[i:i + blk] @ a.t() + lb.item(), dim=1) for i in range(0, N, blk)])
+    diag = s * (a * b).sum(1) + lb.item()
+    ref = 0.5 * ((lse_r - diag).mean() + (lse_c - diag).mean())
+    assert abs(loss.item() - ref.item()) < 2e-5 * abs(ref.item())
+    # gradient rows on a subset: G = (P_row + P_col - 2I) / (2N), d e2 = s G e1, d e1 = s G^T e2
+    idx = torch.arange(0, N, max(N // 256, 1), device=dev())
+    Zr = s * a[idx] @ b.t() + lb.item()
+    G = (torch.exp(Zr - lse_r[idx, None]) + torch.exp(Zr - lse_c[None, :])) / (2 * N)
+    G[torch.arange(idx.numel(), device=dev()), idx] -= 1.0 / N
+    assert relerr(g2[idx], s * G @ b) < 1e-4
+    Zc = s * b[idx] @ a.t() + lb.item()
+    Gt = (torch.exp(Zc - lse_c[idx, None]) + torch.exp(Zc - lse_r[None, :])) / (2 * N)
+    Gt[torch.arange(idx.numel(), device=dev()), idx] -= 1.0 / N
+    assert relerr(g1[idx], s * Gt @ a) < 1e-4
+    assert torch.isfinite(gls).all()
+
+
+@pytest.mark.parametrize("prec,workload", [("fp32", "c4"), ("fused", "c4"), ("fused", "c5"), ("fp32", "c2")])
+def test_data_parallel_parity_on_gpus(prec, workload):
+    """R-GPU data-parallel loss / flat gradient == one GPU on the concatenated global batch (scripts/dp_parity.py, NCCL), for
+    every R in {2, 4, 8} that fits the visible devices; SyncBN (c5) and the classifier head's global normalisation (c2) included."""
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        pytest.skip("needs more than one GPU")
+    for world in (r for r in (2, 4, 8) if r <= n_dev):
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                            "--master-port", str(29500 + world), os.path.join(ROOT, "scripts", "dp_parity.py"), prec, workload],
+                           capture_output=True, text=True, timeout=600, cwd=ROOT)
+        assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
+        assert "-> OK" in r.stdout, r.stdout[-500:]
