@@ -291,6 +291,12 @@ int mvn_weighted_ce_bwd(const float* logits, const int64_t* labels, const float*
 int mvn_mse_fwd(const float* pred, const float* target, int n, float* loss, void* stream);
 int mvn_mse_bwd(const float* pred, const float* target, int n, const float* grad_out, float* dpred, void* stream);
 
+/* "meta" modality input (src/models_multimodal.py:295-304): out[b] = [ class_emb[cls_b] (half floats) | redshift_b repeated half times ];
+ * the backward is the gradient of the embedding table, dclass_emb[c] = sum of dout[b, :half] over rows with cls_b == c (overwritten). */
+int mvn_meta_input_fwd(const float* class_emb, const int64_t* cls, const float* redshift, int B, int half, int n_classes,
+                       float* out, void* stream);
+int mvn_meta_input_bwd(const float* dout, const int64_t* cls, int B, int half, int n_classes, float* dclass_emb, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * A13: torch.optim.RAdam step on a flat buffer (coupled L2 weight decay).  src/models_multimodal.py:306-310.
  * Host passes the per-step scalars: bias_correction1 = 1-beta1^t, sqrt_bias_correction2 = sqrt(1-beta2^t),

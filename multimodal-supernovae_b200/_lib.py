@@ -81,6 +81,8 @@ _SIGS = {
     "mvn_weighted_ce_bwd": (c_int, [P, P, P, c_int, c_int, P, P, P, P]),
     "mvn_mse_fwd": (c_int, [P, P, c_int, P, P]),
     "mvn_mse_bwd": (c_int, [P, P, c_int, P, P, P]),
+    "mvn_meta_input_fwd": (c_int, [P, P, P, c_int, c_int, c_int, P, P]),
+    "mvn_meta_input_bwd": (c_int, [P, P, c_int, c_int, c_int, P, P]),
     "mvn_radam_step": (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, c_float, c_float, P]),
     "mvn_radam_step_dev": (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, P, P, P]),
     "mvn_set_step_counter": (None, [P]),

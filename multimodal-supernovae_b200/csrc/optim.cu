@@ -206,6 +206,40 @@ extern "C" int mvn_mse_bwd(const float* pred, const float* target, int n, const 
     MVN_LAUNCH_CHECK();
     return 0;
 }
+// meta modality input (src/models_multimodal.py:295-304): row b = [ class_emb[cls_b] | redshift_b repeated `half` times ]
+__global__ void meta_input_fwd_kernel(const float* __restrict__ emb, const int64_t* __restrict__ cls, const float* __restrict__ red, int B, int half,
+                                      int n_classes, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * 2 * half) return;
+    const int b = i / (2 * half), d = i % (2 * half);
+    long long c = cls[b];
+    c = c < 0 ? 0 : (c >= n_classes ? n_classes - 1 : c);
+    out[i] = d < half ? emb[c * half + d] : red[b];
+}
+// d class_emb[c, d] = sum over the batch rows with cls == c (fixed order: deterministic)
+__global__ void meta_input_bwd_kernel(const float* __restrict__ dout, const int64_t* __restrict__ cls, int B, int half, int n_classes,
+                                      float* __restrict__ demb) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_classes * half) return;
+    const int c = i / half, d = i % half;
+    float s = 0.f;
+    for (int b = 0; b < B; ++b)
+        if (cls[b] == c) s += dout[(size_t)b * 2 * half + d];
+    demb[i] = s;
+}
+extern "C" int mvn_meta_input_fwd(const float* class_emb, const int64_t* cls, const float* redshift, int B, int half, int n_classes, float* out, void* stream) {
+    MVN_CHECK_ARG(class_emb && cls && redshift && out && B > 0 && half > 0 && n_classes > 0, "meta_input_fwd: bad arguments");
+    meta_input_fwd_kernel<<<cdiv(B * 2 * half, 256), 256, 0, (cudaStream_t)stream>>>(class_emb, cls, redshift, B, half, n_classes, out);
+    MVN_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int mvn_meta_input_bwd(const float* dout, const int64_t* cls, int B, int half, int n_classes, float* dclass_emb, void* stream) {
+    MVN_CHECK_ARG(dout && cls && dclass_emb && B > 0 && half > 0 && n_classes > 0, "meta_input_bwd: bad arguments");
+    meta_input_bwd_kernel<<<cdiv(n_classes * half, 128), 128, 0, (cudaStream_t)stream>>>(dout, cls, B, half, n_classes, dclass_emb);
+    MVN_LAUNCH_CHECK();
+    return 0;
+}
+
 // retrieval curve: counts[t] = #{j : rank_j < k_thr[t]}  (get_ROC_data's "idx in idx_sorted[:int(threshold * N)]" summed over sources)
 __global__ void __launch_bounds__(256) rank_curve_kernel(const int32_t* __restrict__ ranks, int N, const int32_t* __restrict__ k_thr, int n_thr,
                                                          int32_t* __restrict__ counts) {

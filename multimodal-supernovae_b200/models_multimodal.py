@@ -290,7 +290,7 @@ class LightCurveImageCLIP(_Base):
                                             normalize=normalize, gbuf=self._gbuf, goff=g.offsets[i0])
 
     def _meta_embed(self, classification, redshift, normalize: bool):
-        x_meta = torch.concat([self.class_emb(classification), redshift.unsqueeze(1).repeat(1, self.len_meta_input // 2)], dim=-1)
+        x_meta = ops.MetaInputFn.apply(self.class_emb.weight, classification, redshift)      # [class_emb[cls] | redshift repeated], one kernel
         z = self.meta_encoder(x_meta)
         return ops.L2NormFn.apply(z) if normalize else z
 
@@ -433,3 +433,67 @@ class LightCurveImageCLIP(_Base):
                     self.log(f"AUC_val{count}", get_AUC(embs[i], embs[j]), on_epoch=True, on_step=False, prog_bar=True, logger=True)
                     count += 1
         self.embs_list = None
+
+
+class ClipMLP(_Base):
+    """reference: src/models_multimodal.py:859-1060 -- a (pre-trained) CLIP backbone with an MLP head for redshift regression or
+    classification (finetune_clip.py).  The backbone's embeddings come from the fused encoder calls, the head from the per-op
+    kernels; same constructor arguments, state_dict keys (`clip_model.*`, `mlp_model.*`) and training_step as the reference."""
+
+    def __init__(self, clip_model, mlp_kwargs, optimizer_kwargs, lr, combinations=["lightcurve"], regression=True,
+                 classification=False, n_classes=5):
+        super().__init__()
+        enc_dim = 0
+        if "lightcurve" in combinations:
+            enc_dim += clip_model.lightcurve_projection.out_features
+        if "spectral" in combinations:
+            enc_dim += clip_model.spectral_projection.out_features
+        mlp_kwargs["input_dim"] = enc_dim
+        self.clip_model = clip_model
+        self.mlp_model = MLP(**mlp_kwargs)
+        self.optimizer_kwargs = optimizer_kwargs
+        self.lr = lr
+        self.combinations = combinations
+        self.regression = regression
+        self.classification = classification
+        self.n_classes = n_classes
+        self.y_pred, self.y_true = [], []
+        self.track_predictions = False
+
+    def forward(self, x_lc=None, t_lc=None, mask_lc=None, x_sp=None, t_sp=None, mask_sp=None):
+        x = []
+        if "lightcurve" in self.combinations:
+            x.append(self.clip_model.lightcurve_embeddings_with_projection(x_lc, t_lc, mask_lc))
+        if "spectral" in self.combinations:
+            x.append(self.clip_model.spectral_embeddings_with_projection(x_sp, t_sp, mask_sp))
+        x = torch.cat(x, dim=-1) if len(x) > 1 else x[0]
+        return self.mlp_model(x)
+
+    def configure_optimizers(self):
+        # the reference's torch.optim.RAdam over backbone + head (src/models_multimodal.py:923-927); the parameters are views of
+        # flat buffers, which torch's foreach implementation updates in place
+        return {"optimizer": torch.optim.RAdam(self.parameters(), lr=self.lr, **self.optimizer_kwargs)}
+
+    def training_loss(self, batch):
+        _, x_lc, t_lc, mask_lc, x_sp, t_sp, mask_sp, redshift, classification = batch
+        x = self(x_lc, t_lc, mask_lc, x_sp, t_sp, mask_sp)
+        if self.regression:
+            if self.track_predictions:
+                self.y_pred.append(x.flatten()); self.y_true.append(redshift)
+            return ops.dp_weighted_mean(ops.MSEFn.apply(x.squeeze(), redshift), float(redshift.numel()))
+        if self.classification:
+            w = {5: [0.3, 0.08, 1.0, 0.01, 0.2], 3: [0.33, 0.06, 1.0]}.get(self.n_classes, [1.0] * self.n_classes)
+            cw = getattr(self, "_class_w", None)
+            if cw is None or cw.device != x.device:
+                cw = torch.tensor(w, dtype=torch.float32, device=x.device)
+                self._class_w = cw
+            if self.track_predictions:
+                self.y_pred.append(x); self.y_true.append(classification)
+            loss, wsum = ops.WeightedCEFn.apply(x.squeeze(), classification, cw)
+            return ops.dp_weighted_mean(loss, wsum)
+        raise ValueError("ClipMLP needs regression=True or classification=True")
+
+    def training_step(self, batch, batch_idx):
+        loss = self.training_loss(batch)
+        self.log("train_loss", loss, on_epoch=True, on_step=False, prog_bar=True, logger=True)
+        return loss

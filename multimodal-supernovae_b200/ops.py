@@ -773,6 +773,36 @@ def dp_weighted_mean(loss_local: torch.Tensor, weight_local) -> torch.Tensor:
     return _DPWeightedMeanFn.apply(loss_local, weight_local.to(loss_local.dtype), grp)
 
 
+class MetaInputFn(torch.autograd.Function):
+    """[class_emb[cls] | redshift repeated] (src/models_multimodal.py:295-304) as one gather kernel; backward = the embedding
+    table's gradient (deterministic per-class sums)."""
+
+    @staticmethod
+    def forward(ctx, class_emb, cls, redshift):
+        L = lib()
+        w = _req(class_emb, "class_emb.weight")
+        cls = cls.long().contiguous()
+        red = _req(redshift.float(), "redshift")
+        B, (n_classes, half) = cls.numel(), w.shape
+        out = torch.empty(B, 2 * half, dtype=torch.float32, device=w.device)
+        check(L.mvn_meta_input_fwd(_p(w), _p(cls), _p(red), B, half, n_classes, _p(out), _stream()), "meta_input_fwd")
+        _count(1)
+        ctx.save_for_backward(cls)
+        ctx.dims = (B, half, n_classes)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = lib()
+        (cls,) = ctx.saved_tensors
+        B, half, n_classes = ctx.dims
+        dout = _req(dout, "grad_output")
+        dw = torch.empty(n_classes, half, dtype=torch.float32, device=dout.device)
+        check(L.mvn_meta_input_bwd(_p(dout), _p(cls), B, half, n_classes, _p(dw), _stream()), "meta_input_bwd")
+        _count(1)
+        return dw, None, None
+
+
 def retrieval_ranks(e1: torch.Tensor, e2: torch.Tensor) -> torch.Tensor:
     L = lib()
     e1 = _req(e1, "embs1"); e2 = _req(e2, "embs2")

@@ -98,3 +98,60 @@ def test_two_rank_clip_loss_matches_single_process_oracle():
             assert torch.allclose(torch.tensor(grads[m], dtype=torch.float64), embs[m].grad[rank * n:(rank + 1) * n], atol=1e-12)
         assert abs(flat[0] - ls.grad.item()) < 1e-12
         assert abs(flat[1]) < 1e-12 and abs(lb.grad.item()) < 1e-12      # logit_bias: zero gradient
+
+
+def _heads_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from maven_b200 import ops
+    ops.set_data_parallel_group(dist.group.WORLD)
+    torch.manual_seed(1)
+    n_per = [5, 3]                                                     # unequal shards: the weights, not the rank count, normalise
+    logits = torch.randn(sum(n_per), 5, dtype=torch.float64)
+    labels = torch.randint(0, 5, (sum(n_per),))
+    w = torch.tensor([0.3, 0.08, 1.0, 0.01, 0.2], dtype=torch.float64)
+    pred = torch.randn(sum(n_per), dtype=torch.float64); tgt = torch.randn(sum(n_per), dtype=torch.float64)
+    lo = sum(n_per[:rank]); hi = lo + n_per[rank]
+    lg = logits[lo:hi].clone().requires_grad_()
+    local_ce = torch.nn.functional.cross_entropy(lg, labels[lo:hi], weight=w)           # what mvn_weighted_ce_fwd returns per rank
+    ce = ops.dp_weighted_mean(local_ce, w[labels[lo:hi]].sum())
+    ce.backward()
+    pr = pred[lo:hi].clone().requires_grad_()
+    mse = ops.dp_weighted_mean(torch.nn.functional.mse_loss(pr, tgt[lo:hi]), float(hi - lo))
+    mse.backward()
+    q.put((rank, ce.item(), lg.grad.tolist(), mse.item(), pr.grad.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_heads_match_single_process():
+    """MSE / weighted-CE heads under data parallelism == the single-process loss on the concatenated batch, and the per-rank
+    gradients are the corresponding rows of the global gradient (so the SUM all-reduce of parameter gradients is exact)."""
+    world = 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_heads_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.manual_seed(1)
+    n_per = [5, 3]
+    logits = torch.randn(sum(n_per), 5, dtype=torch.float64, requires_grad=True)
+    labels = torch.randint(0, 5, (sum(n_per),))
+    w = torch.tensor([0.3, 0.08, 1.0, 0.01, 0.2], dtype=torch.float64)
+    pred = torch.randn(sum(n_per), dtype=torch.float64, requires_grad=True); tgt = torch.randn(sum(n_per), dtype=torch.float64)
+    ce = torch.nn.functional.cross_entropy(logits, labels, weight=w); ce.backward()
+    mse = torch.nn.functional.mse_loss(pred, tgt); mse.backward()
+    for rank, ce_r, dlg, mse_r, dpr in res:
+        lo = sum(n_per[:rank]); hi = lo + n_per[rank]
+        assert abs(ce_r - ce.item()) < 1e-12 and abs(mse_r - mse.item()) < 1e-12
+        assert torch.allclose(torch.tensor(dlg, dtype=torch.float64), logits.grad[lo:hi], atol=1e-12)
+        assert torch.allclose(torch.tensor(dpr, dtype=torch.float64), pred.grad[lo:hi], atol=1e-12)

@@ -161,3 +161,29 @@ def test_device_augment_field_orders_match_reference_tuple_lengths():
         if "spec" in fields:
             i = fields.index("spec")
             assert fields[i:i + 4] == ("spec", "freq", "maskspec", "specerr")
+
+
+def test_oracle_auc_matches_reference_fixture():
+    """N3 oracle pinned to get_ROC_data / get_AUC outputs of the unmodified reference (tests/golden/make_golden_r2.py)."""
+    import numpy as np
+    from conftest import load_golden
+    from oracle import maven_oracle as O
+    for name in ("auc", "auc_small"):
+        g = load_golden(name)
+        thr, frac = O.roc_data(g["e1"], g["e2"])
+        assert np.array_equal(thr, g["thresholds"].numpy()) and np.array_equal(frac, g["fraction_correct"].numpy())
+        assert abs(O.auc(g["e1"], g["e2"]) - float(g["auc"])) < 1e-12
+
+
+def test_device_augment_ignores_meta_and_rejects_unknown():
+    from maven_b200.augment import DeviceAugment
+    a = DeviceAugment(["lightcurve", "spectral", "meta"], 0.1, 1.0)
+    assert a.fields == DeviceAugment(["lightcurve", "spectral"], 0.1, 1.0).fields
+    with pytest.raises(ValueError):
+        DeviceAugment(["meta"], 0.1, 1.0)
+
+
+def test_dp_weighted_mean_is_identity_without_group():
+    from maven_b200 import ops
+    x = torch.tensor(3.0, requires_grad=True)
+    assert ops.dp_weighted_mean(x, 5.0) is x
