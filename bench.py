@@ -355,6 +355,73 @@ def reference_eager_on_gpu(wl, dropout, dev, B=256, steps=3):
 
 
 # --------------------------------------------------------------------------------------------------
+def c5_sweep(args, world, rank, dev, L):
+    """BASELINE.json configs[4]: the large-global-batch trimodal CLIP (light curve + spectra + image, 3 pairs, all-gathered
+    negatives) swept over the global batch 1k-64k.  Every size is a few eager steps (forward + backward + gradient all-reduce +
+    RAdam) timed on the device; the CLIP-loss share comes from CUDA events around the loss kernels in a separate pass.
+    Runs after the headline measurement and never fails it: an exception is recorded in the result instead."""
+    import ctypes
+    import torch.distributed as dist
+    from maven_b200.models_multimodal import LightCurveImageCLIP
+    from maven_b200.transformer_utils import set_precision
+    wl = WORKLOADS["c5"]
+    out = []
+    torch.manual_seed(0)
+    model = set_precision(LightCurveImageCLIP(**model_kwargs(wl, args.dropout)).to(dev).train(), args.precision)
+    opt = model.configure_optimizers()["optimizer"]
+
+    def step(batch):
+        loss = model.training_step(batch, 0)
+        loss.backward()
+        if world > 1:
+            model.reduce_gradients()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    for g in (1024, 2048, 4096, 8192, 16384, 32768, 65536):
+        b = g // world
+        if b * world != g or b < 128 or b > args.sweep_max_per_gpu:
+            continue
+        rec = {"global_batch": g, "per_gpu_batch": b}
+        try:
+            batch = [None if v is None else v.to(dev) for v in make_batch(wl, b, seed=5000 + rank)]
+            for _ in range(2):
+                step(batch)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            n_t = 3
+            ev0.record()
+            for _ in range(n_t):
+                last = step(batch)
+            ev1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([ev0.elapsed_time(ev1) / n_t], dtype=torch.float64, device=dev)
+            L.mvn_prof_enable(1 << 5)                          # CLIP-loss kernels only
+            step(batch)
+            torch.cuda.synchronize()
+            L.mvn_prof_enable(0)
+            ms, cnt = ctypes.c_double(), ctypes.c_longlong()
+            L.mvn_prof_read(5, ctypes.byref(ms), ctypes.byref(cnt))
+            tl = torch.tensor([ms.value], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+            rec.update(ms_per_step=t.item(), samples_per_s=g / (t.item() / 1e3), loss_kernels_ms=tl.item(), loss_share=tl.item() / t.item(),
+                       loss_last=float(last))
+            del batch
+        except Exception as e:                                 # e.g. out of memory at a size this GPU count cannot hold
+            rec["error"] = f"{type(e).__name__}: {str(e)[:160]}"
+            out.append(rec)
+            break
+        out.append(rec)
+        torch.cuda.empty_cache()
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
 def run_gpu(args):
     import ctypes
     import torch.distributed as dist
@@ -388,7 +455,7 @@ def run_gpu(args):
         loss = model.training_step(batch, 0)
         loss.backward()
         if world > 1:
-            dist.all_reduce(model.gather_grads())
+            model.reduce_gradients()
         opt.step()
         opt.zero_grad(set_to_none=True)
         return loss
@@ -526,6 +593,16 @@ def run_gpu(args):
             torch.cuda.synchronize()
             os._exit(0)
 
+    sweep = None
+    if args.sweep:
+        if graphed is not None:
+            del graphed
+        del model, opt, resident
+        torch.cuda.empty_cache()
+        try:
+            sweep = c5_sweep(args, world, rank, dev, L)
+        except Exception as e:
+            sweep = [{"error": f"{type(e).__name__}: {str(e)[:200]}"}]
     if rank != 0:
         finish()
         return
@@ -611,6 +688,9 @@ def run_gpu(args):
     }
     if ref_gpu is not None:
         line["reference_eager_b200"] = ref_gpu
+    if sweep is not None:
+        line["c5_sweep"] = {"workload": WORKLOADS["c5"]["desc"], "launch": "eager launches, 3 timed steps per size, max over ranks",
+                            "precision": args.precision, "sizes": sweep}
     if cpu is not None:
         line["cpu_baseline"] = cpu
     emit(line)
@@ -646,6 +726,8 @@ def main():
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "fused"],
                     help="tf32: tcgen05/mma tensor-core tier (fp32 storage, fp32 accumulate; parity 1e-3); fp32: FFMA tier (parity 1e-5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", dest="sweep", action="store_false", help="skip the C5 large-global-batch sweep that follows the headline measurement")
+    ap.add_argument("--sweep-max-per-gpu", type=int, default=8192, help="largest per-GPU batch of the C5 sweep (activation workspace ~5 GB per 1024 samples)")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="enqueue every kernel from Python instead of replaying the captured step")
     args = ap.parse_args()
     if args.impl == "reference":

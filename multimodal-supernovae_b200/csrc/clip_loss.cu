@@ -249,6 +249,14 @@ __global__ void __launch_bounds__(256) grad_reduce_kernel(const float* __restric
 }
 
 }  // namespace
+
+// clip_loss_tc.cu: the same two passes on tcgen05 (prec >= 1, D == 128)
+bool tc_loss_supported(int n, int N, int D);
+void tc_loss_split(int n, int N, int nc, int* row_tiles, int* nsplit, int* tiles_per_split);
+int launch_lse_tc(const float* R, const float* C, int nr, int N, const float* logit_scale, const float* logit_bias, int tiles_per_split, int row_tiles,
+                  int nsplit, float* pm, float* pl, cudaStream_t st);
+int launch_grad_tc(const float* R, const float* C, int nr, int N, const float* logit_scale, const float* logit_bias, const float* lse_R,
+                   const float* lse_C, int row_offset, int tiles_per_split, int row_tiles, int nsplit, float* dR_part, float* dls_part, cudaStream_t st);
 }  // namespace mvn
 
 using namespace mvn;
@@ -256,8 +264,17 @@ using namespace mvn;
 extern "C" size_t mvn_clip_loss_workspace_bytes(int n, int N, int D) {
     if (n <= 0 || N <= 0 || D <= 0) return 0;
     const Split sp = make_split(n, N);
-    const size_t fwd = (size_t)4 * sp.nsplit * n + n;                                  // pm/pl x 2 directions + terms
-    const size_t bwd = (size_t)2 * sp.nsplit * n * D + (size_t)sp.nsplit * sp.row_tiles;   // dR partials x 2 + dls partials
+    size_t fwd = (size_t)4 * sp.nsplit * n + n;                                  // pm/pl x 2 directions + terms
+    size_t bwd = (size_t)2 * sp.nsplit * n * D + (size_t)sp.nsplit * sp.row_tiles;   // dR partials x 2 + dls partials
+    if (tc_loss_supported(n, N, D)) {                                            // the tensor-core passes split the columns differently
+        int rt, ns, tps;
+        tc_loss_split(n, N, 128, &rt, &ns, &tps);
+        const size_t f2 = (size_t)4 * ns * n + n;
+        tc_loss_split(n, N, 64, &rt, &ns, &tps);
+        const size_t b2 = (size_t)2 * ns * n * D + (size_t)ns * rt;
+        fwd = fwd > f2 ? fwd : f2;
+        bwd = bwd > b2 ? bwd : b2;
+    }
     return (fwd > bwd ? fwd : bwd) * sizeof(float) + 256;
 }
 
@@ -274,13 +291,29 @@ static int check_loss_args(const float* a, const float* b, const float* c, const
 extern "C" int mvn_clip_loss_fwd(const float* e1_local, const float* e2_local, const float* e1_all, const float* e2_all, int n, int N,
                                  int D, int row_offset, const float* logit_scale, const float* logit_bias, float* loss_out,
                                  float* lse_row, float* lse_col, void* workspace, size_t workspace_bytes, int prec, void* stream) {
-    (void)prec;
     MVN_TRY(check_loss_args(e1_local, e2_local, e1_all, e2_all, n, N, D, row_offset, logit_scale, logit_bias, workspace, workspace_bytes));
     MVN_CHECK_ARG(loss_out && lse_row && lse_col, "clip_loss_fwd: null outputs");
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope prof(PROF_LOSS, st);
-    const Split sp = make_split(n, N);
     float* ws = (float*)workspace;
+    if (prec >= 1 && tc_loss_supported(n, N, D)) {
+        int rt, ns, tps;
+        tc_loss_split(n, N, 128, &rt, &ns, &tps);
+        float* pm_r = ws;                        float* pl_r = pm_r + (size_t)ns * n;
+        float* pm_c = pl_r + (size_t)ns * n;     float* pl_c = pm_c + (size_t)ns * n;
+        float* terms = pl_c + (size_t)ns * n;
+        MVN_TRY(launch_lse_tc(e2_local, e1_all, n, N, logit_scale, logit_bias, tps, rt, ns, pm_r, pl_r, st));
+        MVN_TRY(launch_lse_tc(e1_local, e2_all, n, N, logit_scale, logit_bias, tps, rt, ns, pm_c, pl_c, st));
+        count_tier(TIER_TC);
+        lse_finish_kernel<<<cdiv(n * 32, 256), 256, 0, st>>>(pm_r, pl_r, pm_c, pl_c, ns, e1_local, e2_local, n, D, logit_scale, logit_bias,
+                                                             lse_row, lse_col, terms);
+        MVN_LAUNCH_CHECK();
+        sum_kernel<<<1, 1024, 0, st>>>(terms, n, 0.5f / (float)N, nullptr, loss_out);
+        MVN_LAUNCH_CHECK();
+        return 0;
+    }
+    count_tier(TIER_FFMA);
+    const Split sp = make_split(n, N);
     float* pm_r = ws;                       float* pl_r = pm_r + (size_t)sp.nsplit * n;
     float* pm_c = pl_r + (size_t)sp.nsplit * n; float* pl_c = pm_c + (size_t)sp.nsplit * n;
     float* terms = pl_c + (size_t)sp.nsplit * n;
@@ -302,13 +335,34 @@ extern "C" int mvn_clip_loss_bwd(const float* e1_local, const float* e2_local, c
                                  int D, int row_offset, const float* logit_scale, const float* logit_bias, const float* lse_row_all,
                                  const float* lse_col_all, const float* grad_out, float* d_e1_local, float* d_e2_local,
                                  float* d_logit_scale, void* workspace, size_t workspace_bytes, int prec, void* stream) {
-    (void)prec;
     MVN_TRY(check_loss_args(e1_local, e2_local, e1_all, e2_all, n, N, D, row_offset, logit_scale, logit_bias, workspace, workspace_bytes));
     MVN_CHECK_ARG(lse_row_all && lse_col_all && d_e1_local && d_e2_local && d_logit_scale, "clip_loss_bwd: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope prof(PROF_LOSS, st);
-    const Split sp = make_split(n, N);
     float* ws = (float*)workspace;
+    if (prec >= 1 && tc_loss_supported(n, N, D)) {
+        int rt, ns, tps;
+        tc_loss_split(n, N, 64, &rt, &ns, &tps);
+        float* part2 = ws;
+        float* part1 = part2 + (size_t)ns * n * D;
+        float* dls_part = part1 + (size_t)ns * n * D;
+        MVN_TRY(launch_grad_tc(e2_local, e1_all, n, N, logit_scale, logit_bias, lse_row_all + row_offset, lse_col_all, row_offset, tps, rt, ns, part2,
+                               dls_part, st));
+        MVN_TRY(launch_grad_tc(e1_local, e2_all, n, N, logit_scale, logit_bias, lse_col_all + row_offset, lse_row_all, row_offset, tps, rt, ns, part1,
+                               nullptr, st));
+        count_tier(TIER_TC);
+        const size_t ne = (size_t)n * D;
+        const int blocks = (int)((ne + 255) / 256 < 2048 ? (ne + 255) / 256 : 2048);
+        grad_reduce_kernel<<<blocks, 256, 0, st>>>(part2, ns, ne, logit_scale, grad_out, d_e2_local);
+        MVN_LAUNCH_CHECK();
+        grad_reduce_kernel<<<blocks, 256, 0, st>>>(part1, ns, ne, logit_scale, grad_out, d_e1_local);
+        MVN_LAUNCH_CHECK();
+        sum_kernel<<<1, 1024, 0, st>>>(dls_part, ns * rt, 1.0f, grad_out, d_logit_scale);
+        MVN_LAUNCH_CHECK();
+        return 0;
+    }
+    count_tier(TIER_FFMA);
+    const Split sp = make_split(n, N);
     float* part2 = ws;                                        // d_e2 partials  [nsplit][n][D]
     float* part1 = part2 + (size_t)sp.nsplit * n * D;         // d_e1 partials
     float* dls_part = part1 + (size_t)sp.nsplit * n * D;      // [nsplit*row_tiles]

@@ -66,8 +66,7 @@ class GraphedTrainStep:
         loss = self.model.training_step(self.static, 0)
         loss.backward()
         if self.group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(self.model.gather_grads(), group=self.group)
+            self.model.reduce_gradients(self.group)             # encoder segments were launched during the backward (overlap)
         self.optimizer.step()
         return loss
 

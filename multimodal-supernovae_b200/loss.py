@@ -32,6 +32,9 @@ def clip_loss_multimodal(embeddings, logit_scales=1.0, logit_biases=0.0, prec: i
         logit_scales = torch.tensor(float(logit_scales), device=dev)
     if not torch.is_tensor(logit_biases):
         logit_biases = torch.tensor(float(logit_biases), device=dev)
+    if logit_scales.dim() == 0 and logit_biases.dim() == 0 and n >= 2:
+        # one scale / bias for every pair (the model's case): all pairs in one op -> one all-gather of the embeddings, one of the LSEs
+        return ops.ClipLossMultiFn.apply(logit_scales, logit_biases, prec, *embeddings)
     loss_total = 0
     count = 0
     for i in range(n - 1):

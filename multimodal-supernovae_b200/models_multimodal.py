@@ -181,6 +181,8 @@ class LightCurveImageCLIP(_Base):
         self.track_predictions = False      # the reference's epoch-end metric hooks (out of scope) consume these lists
         # One CUDA stream per modality encoder (see _run_modalities); MVN_CONCURRENT=0 keeps everything on the caller's stream.
         self.concurrent_modalities = os.environ.get("MVN_CONCURRENT", "1") != "0"
+        # data parallel: start each encoder's gradient all-reduce as soon as its backward has been enqueued (maven_b200.ops.finish_grad_reduce)
+        self.overlap_grad_reduce = os.environ.get("MVN_OVERLAP_GRADS", "1") != "0"
 
     # ---- flat parameter group over the whole model ---------------------------------------------------------
     # The flat layout is cached between steps (walking ~130 parameters through nn.Module.parameters() costs ~0.7 ms of
@@ -258,6 +260,13 @@ class LightCurveImageCLIP(_Base):
                     p.grad = v
         return gbuf
 
+    def reduce_gradients(self, group=None) -> torch.Tensor:
+        """Data-parallel SUM all-reduce of the flat gradient buffer (call after backward, before the optimizer step): the encoder
+        segments were launched during the backward (see ops.begin_grad_overlap), this waits for them and reduces the rest."""
+        gbuf = self.gather_grads()
+        ops.finish_grad_reduce(gbuf, group)
+        return gbuf
+
     def _new_gbuf(self, g: ops.FlatParams, device):
         if torch.is_grad_enabled():
             # zeros, not empty: slots of parameters that receive no gradient this step (logit_scale of a classifier, a frozen
@@ -265,6 +274,7 @@ class LightCurveImageCLIP(_Base):
             self._gbuf = torch.zeros(g.total, dtype=torch.float32, device=device)
         else:
             self._gbuf = None
+        ops.begin_grad_overlap(self._gbuf if (self.training and self.overlap_grad_reduce) else None)
         return self._gbuf
 
     def _seq_embed(self, which: str, x, t, mask, g, normalize: bool):
@@ -386,7 +396,7 @@ class LightCurveImageCLIP(_Base):
             loss, wsum = ops.WeightedCEFn.apply(x.squeeze(), classification, cw)
             return ops.dp_weighted_mean(loss, wsum)
         if self.loss == "softmax":
-            return clip_loss_multimodal(x, self.logit_scale, self.logit_bias, prec=0)   # 0-dim already: .mean() is the identity
+            return clip_loss_multimodal(x, self.logit_scale, self.logit_bias, prec=min(_prec_of(self), 1))   # 0-dim already: .mean() is the identity
         raise NotImplementedError("maven_b200 builds the softmax CLIP loss only (every reference driver sets loss='softmax')")
 
     def training_step(self, batch, batch_idx):
@@ -415,7 +425,7 @@ class LightCurveImageCLIP(_Base):
                 x = self(x_img, x_lc, t_lc, mask_lc, x_sp, t_sp, mask_sp, redshift, classification)
                 for i in range(len(self.embs_list)):
                     self.embs_list[i].append(x[i])
-                loss = clip_loss_multimodal(x, self.logit_scale, self.logit_bias, prec=0)
+                loss = clip_loss_multimodal(x, self.logit_scale, self.logit_bias, prec=min(_prec_of(self), 1))
         self.log("val_loss", loss, on_epoch=True, on_step=False, prog_bar=True, logger=True)
         return loss
 

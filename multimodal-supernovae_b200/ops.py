@@ -162,6 +162,7 @@ class SeqEncoderFn(torch.autograd.Function):
         check(L.mvn_seq_encoder_bwd(ctypes.byref(cfg), _p(ctx.pview), _p(ctx.x), _p(dout), _p(g), _p(ctx.ws), ctx.ws.numel(), _stream()),
               "seq_encoder_bwd")
         _count(6 + 12 * cfg.depth + 2)
+        _segment_done(call.gbuf, call.goff, call.count)        # data parallel: this encoder's gradients start their all-reduce now
         needs = ctx.needs_input_grad[4:]
         grp: FlatParams = call.group
         i0, i1 = call.pidx
@@ -549,6 +550,7 @@ class ConvMixerFn(torch.autograd.Function):
                 import torch.distributed as dist
                 dist.all_reduce(sb[s - 1], group=ctx.grp)
         _count(10 + 8 * cfg.depth * 2)
+        _segment_done(call.gbuf, call.goff, call.count)
         needs = ctx.needs_input_grad[2:]
         grp: FlatParams = call.group
         i0, i1 = call.pidx
@@ -609,6 +611,53 @@ def set_data_parallel_group(group):
 
 def get_data_parallel_group():
     return _DP_GROUP
+
+
+# ---- gradient all-reduce overlapped with the backward pass -----------------------------------------------------------
+# The flat gradient buffer is laid out encoder by encoder.  An encoder's backward writes its whole segment in one library
+# call, on the stream its forward ran on; with a data-parallel group set, that segment's all-reduce is launched right there
+# (async: NCCL's stream waits for that encoder's kernels only), so it runs while the other modality's backward is still
+# executing.  finish_grad_reduce() waits for the launched pieces and reduces what is left (heads, logit scale) in one call.
+_GRAD_OVERLAP = {"gbuf": None, "pending": []}
+
+
+def begin_grad_overlap(gbuf: Optional[torch.Tensor]):
+    """Called by the model's forward for every training step: segments of `gbuf` written by fused backward calls from now on are
+    all-reduced as soon as they are complete.  None switches the mechanism off."""
+    _GRAD_OVERLAP["gbuf"] = gbuf if (_DP_GROUP is not None and gbuf is not None) else None
+    _GRAD_OVERLAP["pending"] = []
+
+
+def _segment_done(gbuf: Optional[torch.Tensor], off: int, count: int):
+    if gbuf is None or _GRAD_OVERLAP["gbuf"] is not gbuf or _DP_GROUP is None or count == 0:
+        return
+    import torch.distributed as dist
+    work = dist.all_reduce(gbuf[off:off + count], group=_DP_GROUP, async_op=True)
+    _GRAD_OVERLAP["pending"].append((off, count, work))
+
+
+def finish_grad_reduce(gbuf: torch.Tensor, group=None):
+    """SUM all-reduce of the flat gradient buffer over the data-parallel group: waits for the segments launched during the
+    backward and reduces the remaining ranges.  Equivalent to one dist.all_reduce(gbuf)."""
+    import torch.distributed as dist
+    group = group if group is not None else _DP_GROUP
+    if group is None:
+        return
+    pend = _GRAD_OVERLAP["pending"] if _GRAD_OVERLAP["gbuf"] is gbuf else []
+    done = sorted((o, c) for o, c, _ in pend)
+    for _, _, w in pend:
+        w.wait()
+    pos, rest = 0, []
+    for o, c in done:
+        if o > pos:
+            rest.append((pos, o))
+        pos = max(pos, o + c)
+    if pos < gbuf.numel():
+        rest.append((pos, gbuf.numel()))
+    for a, b in rest:
+        dist.all_reduce(gbuf[a:b], group=group)
+    _GRAD_OVERLAP["pending"] = []
+    _GRAD_OVERLAP["gbuf"] = None
 
 
 def _all_gather_rows(t: torch.Tensor, group) -> torch.Tensor:
@@ -687,6 +736,63 @@ class ClipLossFn(torch.autograd.Function):
         # d_logit_scale is this rank's share: it is summed over ranks by the flat gradient all-reduce like every parameter grad.
         dlb = torch.zeros(lb_shape, dtype=torch.float32, device=e1.device)
         return d1, d2, dls.reshape(ls_shape), dlb, None
+
+
+class ClipLossMultiFn(torch.autograd.Function):
+    """clip_loss_multimodal (src/loss.py:41-65) for M modalities sharing one scalar logit scale / bias: the sum over the
+    M(M-1)/2 pairs with ONE all-gather of all modalities' embeddings, ONE all-gather of all pairs' LSE vectors and ONE
+    all-reduce of the loss (the per-pair form gathers every embedding once per pair it takes part in).  The arithmetic is
+    the same two kernels per pair as ClipLossFn."""
+
+    @staticmethod
+    def forward(ctx, logit_scale, logit_bias, prec: int, *embs):
+        M = len(embs)
+        n, D = embs[0].shape
+        for e in embs:
+            if e.shape != (n, D):
+                raise ValueError(f"clip_loss_multimodal: every modality must be ({n}, {D}), got {tuple(e.shape)}")
+        ls = logit_scale.reshape(1); lb = logit_bias.reshape(1)
+        e_loc = torch.stack(list(embs))                                               # (M, n, D); device / dtype are checked by the kernel calls
+        grp = _DP_GROUP
+        if grp is not None:
+            import torch.distributed as dist
+            rank, world = dist.get_rank(grp), dist.get_world_size(grp)
+            e_all = _all_gather_rows(e_loc.unsqueeze(0), grp).permute(1, 0, 2, 3).reshape(M, world * n, D).contiguous()
+        else:
+            rank, world, e_all = 0, 1, e_loc
+        N, off = n * world, rank * n
+        pairs = [(i, j) for i in range(M - 1) for j in range(i + 1, M)]
+        total = None
+        lses = []
+        for i, j in pairs:
+            loss, lse = _clip_fwd_local(e_loc[i], e_loc[j], e_all[i], e_all[j], n, N, D, off, ls, lb, prec)
+            total = loss if total is None else total + loss
+            lses.append(lse)
+        lse_loc = torch.stack(lses)                                                       # (P, 2, n)
+        if grp is not None:
+            import torch.distributed as dist
+            lse_all = _all_gather_rows(lse_loc.unsqueeze(0), grp).permute(1, 2, 0, 3).reshape(len(pairs), 2, N).contiguous()
+            dist.all_reduce(total, group=grp)
+        else:
+            lse_all = lse_loc
+        ctx.save_for_backward(e_loc, e_all, ls, lb, lse_all)
+        ctx.meta = (M, n, N, D, off, prec, pairs, logit_scale.shape, logit_bias.shape)
+        return total.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        e_loc, e_all, ls, lb, lse_all = ctx.saved_tensors
+        M, n, N, D, off, prec, pairs, ls_shape, lb_shape = ctx.meta
+        g1 = g.reshape(1).contiguous()
+        de = [None] * M
+        dls_tot = None
+        for p, (i, j) in enumerate(pairs):
+            d1, d2, dls = _clip_bwd_local(e_loc[i], e_loc[j], e_all[i], e_all[j], n, N, D, off, ls, lb, lse_all[p], g1, prec)
+            de[i] = d1 if de[i] is None else de[i] + d1
+            de[j] = d2 if de[j] is None else de[j] + d2
+            dls_tot = dls if dls_tot is None else dls_tot + dls
+        dlb = torch.zeros(lb_shape, dtype=lb.dtype, device=e_loc.device)              # identically zero under the two softmaxes
+        return (dls_tot.reshape(ls_shape), dlb, None) + tuple(de)
 
 
 class WeightedCEFn(torch.autograd.Function):

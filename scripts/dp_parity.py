@@ -34,8 +34,7 @@ def main():
     m = build()
     loss = m.training_step(shard, 0)
     loss.backward()
-    g = m.gather_grads().clone()
-    dist.all_reduce(g)
+    g = m.reduce_gradients().clone()                                       # overlapped per-encoder segments + the rest
     ops.set_data_parallel_group(None)
     ok = True
     if rank == 0:

@@ -155,3 +155,41 @@ def test_two_rank_heads_match_single_process():
         assert abs(ce_r - ce.item()) < 1e-12 and abs(mse_r - mse.item()) < 1e-12
         assert torch.allclose(torch.tensor(dlg, dtype=torch.float64), logits.grad[lo:hi], atol=1e-12)
         assert torch.allclose(torch.tensor(dpr, dtype=torch.float64), pred.grad[lo:hi], atol=1e-12)
+
+
+def _overlap_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from maven_b200 import ops
+    ops.set_data_parallel_group(dist.group.WORLD)
+    torch.manual_seed(rank)
+    g = torch.randn(97)
+    mine = g.clone()
+    ops.begin_grad_overlap(g)
+    ops._segment_done(g, 10, 20)          # "encoder A finished its backward": its segment starts reducing now
+    ops._segment_done(g, 50, 7)           # encoder B
+    ops.finish_grad_reduce(g)             # waits for both, reduces [0,10), [30,50), [57,97)
+    q.put((rank, mine.tolist(), g.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_overlapped_segment_reduce_equals_one_all_reduce():
+    world = 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_overlap_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    total = torch.tensor(res[0][1]) + torch.tensor(res[1][1])
+    for _, _, got in res:
+        assert torch.allclose(torch.tensor(got), total, atol=1e-6)

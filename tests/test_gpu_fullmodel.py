@@ -66,7 +66,8 @@ def test_training_step_reduced_precision_vs_oracle(workload, tier):
 
 
 @pytest.mark.parametrize("N", [8192, 65536])
-def test_clip_loss_large_global_batch(N):
+@pytest.mark.parametrize("prec", [0, 1])
+def test_clip_loss_large_global_batch(N, prec):
     """N x N never materialised: loss + gradients of the streamed kernels at the global batches of config C5 against an fp64
     reference that needs only O(N) memory per row block (LSE over column blocks)."""
     from maven_b200.loss import clip_loss
@@ -77,7 +78,7 @@ def test_clip_loss_large_global_batch(N):
     ls, lb = torch.tensor(math.log(19.55)), torch.tensor(-10.0)
     e1c, e2c = e1.to(dev()).requires_grad_(), e2.to(dev()).requires_grad_()
     lsc, lbc = ls.to(dev()).requires_grad_(), lb.to(dev()).requires_grad_()
-    loss = clip_loss(e1c, e2c, lsc, lbc)
+    loss = clip_loss(e1c, e2c, lsc, lbc, prec=prec)                  # prec 1: similarity tiles on tcgen05 (clip_loss_tc.cu)
     g1, g2, gls, _ = torch.autograd.grad(loss, [e1c, e2c, lsc, lbc])
     # fp64 reference on the GPU, blocked: Z = s * e2 e1^T + b  (rows: e2, columns: e1)
     s = math.exp(ls.item())
@@ -87,18 +88,20 @@ def test_clip_loss_large_global_batch(N):
     lse_c = torch.cat([torch.logsumexp(s * b[i:i + blk] @ a.t() + lb.item(), dim=1) for i in range(0, N, blk)])
     diag = s * (a * b).sum(1) + lb.item()
     ref = 0.5 * ((lse_r - diag).mean() + (lse_c - diag).mean())
-    assert abs(loss.item() - ref.item()) < 2e-5 * abs(ref.item())
+    tol_l, tol_g = (2e-5, 1e-4) if prec == 0 else (2e-4, 2e-3)
+    assert abs(loss.item() - ref.item()) < tol_l * abs(ref.item())
     # gradient rows on a subset: G = (P_row + P_col - 2I) / (2N), d e2 = s G e1, d e1 = s G^T e2
     idx = torch.arange(0, N, max(N // 256, 1), device=dev())
     Zr = s * a[idx] @ b.t() + lb.item()
     G = (torch.exp(Zr - lse_r[idx, None]) + torch.exp(Zr - lse_c[None, :])) / (2 * N)
     G[torch.arange(idx.numel(), device=dev()), idx] -= 1.0 / N
-    assert relerr(g2[idx], s * G @ b) < 1e-4
+    assert relerr(g2[idx], s * G @ b) < tol_g
     Zc = s * b[idx] @ a.t() + lb.item()
     Gt = (torch.exp(Zc - lse_c[idx, None]) + torch.exp(Zc - lse_r[None, :])) / (2 * N)
     Gt[torch.arange(idx.numel(), device=dev()), idx] -= 1.0 / N
-    assert relerr(g1[idx], s * Gt @ a) < 1e-4
-    assert torch.isfinite(gls).all()
+    assert relerr(g1[idx], s * Gt @ a) < tol_g
+    gls_ref = (G * (Zr - lb.item())).sum() * (N / idx.numel())        # subset estimate of sum G (Z - b): order of magnitude check only
+    assert torch.isfinite(gls).all() and abs(gls.item()) < 10 * abs(gls_ref.item()) + 1e-3
 
 
 @pytest.mark.parametrize("prec,workload", [("fp32", "c4"), ("fused", "c4"), ("fused", "c5"), ("fp32", "c2")])

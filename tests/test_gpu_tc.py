@@ -175,3 +175,39 @@ def test_tc_attention_fwd_bwd(L, E, H, lens):
     assert relerr(out, oref) < TOL_TC
     assert torch.isfinite(dqkv).all()
     assert relerr(dqkv, ref.grad) < 2e-3
+
+
+@pytest.mark.parametrize("N", [37, 128, 300, 1024, 2500])
+def test_tc_clip_loss(N):
+    """symmetric InfoNCE with the similarity tiles on tcgen05 (clip_loss_tc.cu) vs the fp64 oracle: 2-modality and 3-modality
+    (one op for all pairs), incl. N below one 128-row tile, ragged last tiles and the d logit_scale reduction."""
+    from maven_b200 import _lib
+    from maven_b200.loss import clip_loss, clip_loss_multimodal
+    from oracle import maven_oracle as O
+    Lb = _lib.lib()
+    gen = torch.Generator().manual_seed(N)
+    base = torch.randn(N, 128, generator=gen)
+    e = [torch.nn.functional.normalize(base + 0.8 * torch.randn(N, 128, generator=gen), dim=-1) for _ in range(3)]
+    ls, lb = torch.tensor(math.log(19.55)), torch.tensor(-10.0)
+    er = [t.double().requires_grad_() for t in e]
+    lsr, lbr = ls.double().requires_grad_(), lb.double().requires_grad_()
+    l2r = O.clip_loss(er[0], er[1], lsr, lbr)
+    g2r = torch.autograd.grad(l2r, [er[0], er[1], lsr])
+    l3r = O.clip_loss_multimodal(er, lsr, lbr)
+    g3r = torch.autograd.grad(l3r, er + [lsr])
+    ec = [t.to(dev()).requires_grad_() for t in e]
+    lsc, lbc = ls.to(dev()).requires_grad_(), lb.to(dev()).requires_grad_()
+    Lb.mvn_tier_reset()
+    l2 = clip_loss(ec[0], ec[1], lsc, lbc, prec=1)
+    g2 = torch.autograd.grad(l2, [ec[0], ec[1], lsc, lbc])
+    assert Lb.mvn_tier_count(1) == 2 and Lb.mvn_tier_count(0) == 0           # forward + backward ran on the tensor-core kernels
+    assert abs(l2.item() - l2r.item()) < 2e-4 * abs(l2r.item())
+    assert relerr(g2[0], g2r[0]) < 2e-3 and relerr(g2[1], g2r[1]) < 2e-3
+    assert abs(g2[2].item() - g2r[2].item()) < 2e-3 * abs(g2r[2].item()) + 1e-5
+    assert g2[3].item() == 0.0
+    l3 = clip_loss_multimodal(ec, lsc, lbc, prec=1)
+    g3 = torch.autograd.grad(l3, ec + [lsc])
+    assert abs(l3.item() - l3r.item()) < 2e-4 * abs(l3r.item())
+    for i in range(3):
+        assert relerr(g3[i], g3r[i]) < 2e-3
+    assert abs(g3[3].item() - g3r[3].item()) < 2e-3 * abs(g3r[3].item()) + 1e-5
