@@ -670,7 +670,7 @@ def run_gpu(args):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": ct["bound"], "kernel_class": top, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                     "traffic": tr.get(top), "traffic_source": traffic_all.get("_source"),
+                     "traffic": tr.get(top), "traffic_source": tr.get("_source"),
                      "algorithmic_per_launch": per_launch, "avg_launch_ms": avg_ms, "peak_source": src,
                      "frac_hbm": ct["frac_hbm"], "launches_timed": prof_tot[top][1], "class_ms_per_step": ct["ms"],
                      "step_frac_of_tensor_peak": {"padded": step_padded / tf, "executed": fl["executed_train"] / (ms_per_step / 1e3) / 1e12 / tf,

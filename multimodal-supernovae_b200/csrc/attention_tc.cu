@@ -252,8 +252,8 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
     constexpr int LD = HD + 4;
     __shared__ __align__(16) float As[CH * LD];     // phase 1: K        phase 2: Q
     __shared__ __align__(16) float Bs[CH * LD];     // phase 1: V        phase 2: dO
-    __shared__ __align__(8) float lse_s[CH];        // phase 2: lse_i * log2e (+inf on padding rows)
-    __shared__ __align__(8) float D_s[CH];                       // phase 2: D_i = dO_i . O_i
+    __shared__ float lse_s[CH];                     // phase 2: lse_i * log2e (+inf on padding rows)
+    __shared__ float D_s[CH];                       // phase 2: D_i = dO_i . O_i
     const int b = blockIdx.x / H, h = blockIdx.x % H;
     const int r0 = cu[b], n = cu[b + 1] - r0;
     if (n <= 0) return;
@@ -292,42 +292,33 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
             const int k0c = c * CH, kn = min(CH, n - k0c);
             if (nchunks > 1 || rd == 0) {
                 __syncthreads();
-                load_slice32<HD>(As, base, ld, E + h * HD, k0c, kn, 1.0f);
-                load_slice32<HD>(Bs, base, ld, 2 * E + h * HD, k0c, kn, 1.0f);
+                load_slice<HD>(As, base, ld, E + h * HD, k0c, kn, 1.0f);
+                load_slice<HD>(Bs, base, ld, 2 * E + h * HD, k0c, kn, 1.0f);
                 __syncthreads();
             }
             if (!active) continue;
-            // guard-free blocks of 4 key tiles (32 keys; K / V rows past the sequence end are zero in shared memory, so whatever
-            // finite dS they get multiplies a zero row in the dQ MMA): four independent S / dP chains in flight per warp
-            const int kpad = (kn + 31) & ~31;
-            for (int kb = 0; kb < kpad; kb += 32) {
-                constexpr int NT = 4;
-                float s[NT][4], dp[NT][4];
+            const int ntile = (kn + 7) >> 3;
+            for (int j = 0; j < ntile; ++j) {
+                const int key0 = j * 8;
+                float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+                float kf[HD / 4], vf[HD / 4];
+                lds_vec<HD>(kf, As + (key0 + g) * LD + t * (HD / 4));
+                lds_vec<HD>(vf, Bs + (key0 + g) * LD + t * (HD / 4));
 #pragma unroll
-                for (int j = 0; j < NT; ++j) {
-                    float kf[HD / 4], vf[HD / 4];
-                    lds_vec<HD>(kf, As + (kb + j * 8 + g) * LD + t * (HD / 4));
-                    lds_vec<HD>(vf, Bs + (kb + j * 8 + g) * LD + t * (HD / 4));
-                    s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-                    dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
-#pragma unroll
-                    for (int ks = 0; ks < HD / 8; ++ks) {
-                        mma_tf32(s[j], qa[ks], kf[2 * ks], kf[2 * ks + 1]);
-                        mma_tf32(dp[j], ga[ks], vf[2 * ks], vf[2 * ks + 1]);
-                    }
+                for (int ks = 0; ks < HD / 8; ++ks) {
+                    mma_tf32(s, qa[ks], kf[2 * ks], kf[2 * ks + 1]);
+                    mma_tf32(dp, ga[ks], vf[2 * ks], vf[2 * ks + 1]);
                 }
+                // no key mask needed: rows of K past the sequence end are zero-filled in shared memory, so whatever (finite) dS
+                // they get multiplies a zero row in the dQ MMA below
+                const float p0 = ex2(s[0] - L_lo), p1 = ex2(s[1] - L_lo);
+                const float p2 = ex2(s[2] - L_hi), p3 = ex2(s[3] - L_hi);
+                const float da[4] = {tf32r(p0 * (dp[0] - D_lo)), tf32r(p2 * (dp[2] - D_hi)), tf32r(p1 * (dp[1] - D_lo)), tf32r(p3 * (dp[3] - D_hi))};
+                float k0[HD / 8], k1[HD / 8];                      // output columns relabelled by sigma
+                lds_half<HD>(k0, As + (key0 + 2 * t) * LD + g * (HD / 8));
+                lds_half<HD>(k1, As + (key0 + 2 * t + 1) * LD + g * (HD / 8));
 #pragma unroll
-                for (int j = 0; j < NT; ++j) {
-                    const float p0 = ex2(s[j][0] - L_lo), p1 = ex2(s[j][1] - L_lo);
-                    const float p2 = ex2(s[j][2] - L_hi), p3 = ex2(s[j][3] - L_hi);
-                    const float da[4] = {tf32r(p0 * (dp[j][0] - D_lo)), tf32r(p2 * (dp[j][2] - D_hi)), tf32r(p1 * (dp[j][1] - D_lo)),
-                                         tf32r(p3 * (dp[j][3] - D_hi))};
-                    float k0[HD / 8], k1[HD / 8];                      // output columns relabelled by sigma
-                    lds_half<HD>(k0, As + (kb + j * 8 + 2 * t) * LD + g * (HD / 8));
-                    lds_half<HD>(k1, As + (kb + j * 8 + 2 * t + 1) * LD + g * (HD / 8));
-#pragma unroll
-                    for (int nt = 0; nt < HD / 8; ++nt) mma_tf32(dq[nt], da, k0[nt], k1[nt]);
-                }
+                for (int nt = 0; nt < HD / 8; ++nt) mma_tf32(dq[nt], da, k0[nt], k1[nt]);
             }
         }
         if (!active) continue;
@@ -349,9 +340,9 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
             const int q0c = c * CH, qn = min(CH, n - q0c);
             if (nchunks > 1 || rd == 0) {
                 __syncthreads();                    // also orders phase-1 readers of As/Bs before the overwrite
-                load_slice32<HD>(As, base, ld, h * HD, q0c, qn, 1.0f);
-                load_slice32<HD>(Bs, gbase, (size_t)E, 0, q0c, qn, 1.0f);
-                const int pad = (qn + 31) & ~31;
+                load_slice<HD>(As, base, ld, h * HD, q0c, qn, 1.0f);
+                load_slice<HD>(Bs, gbase, (size_t)E, 0, q0c, qn, 1.0f);
+                const int pad = (qn + 7) & ~7;
                 for (int i = threadIdx.x; i < pad; i += ATC_THREADS) {
                     float Di = 0.f, Li = INFINITY;
                     if (i < qn) {
@@ -368,42 +359,32 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
                 __syncthreads();
             }
             if (!active) continue;
-            // guard-free blocks of 4 query tiles: padding queries carry lse = +inf (p = 0) and zero Q / dO rows
-            const int qpad = (qn + 31) & ~31;
-            for (int qb = 0; qb < qpad; qb += 32) {
-                constexpr int NT = 4;
-                float s[NT][4], dp[NT][4];                                  // transposed tiles: rows = keys, cols = queries
+            const int ntile = (qn + 7) >> 3;
+            for (int j = 0; j < ntile; ++j) {
+                const int qq = j * 8;
+                float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};      // transposed tiles: rows = keys, cols = queries
+                float qf[HD / 4], gf[HD / 4];
+                lds_vec<HD>(qf, As + (qq + g) * LD + t * (HD / 4));
+                lds_vec<HD>(gf, Bs + (qq + g) * LD + t * (HD / 4));
 #pragma unroll
-                for (int j = 0; j < NT; ++j) {
-                    float qf[HD / 4], gf[HD / 4];
-                    lds_vec<HD>(qf, As + (qb + j * 8 + g) * LD + t * (HD / 4));
-                    lds_vec<HD>(gf, Bs + (qb + j * 8 + g) * LD + t * (HD / 4));
-                    s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-                    dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f;
-#pragma unroll
-                    for (int ks = 0; ks < HD / 8; ++ks) {
-                        mma_tf32(s[j], ka[ks], qf[2 * ks], qf[2 * ks + 1]);
-                        mma_tf32(dp[j], va[ks], gf[2 * ks], gf[2 * ks + 1]);
-                    }
+                for (int ks = 0; ks < HD / 8; ++ks) {
+                    mma_tf32(s, ka[ks], qf[2 * ks], qf[2 * ks + 1]);
+                    mma_tf32(dp, va[ks], gf[2 * ks], gf[2 * ks + 1]);
                 }
+                const int qc = qq + 2 * t;
+                const float L0 = lse_s[qc], L1 = lse_s[qc + 1], D0 = D_s[qc], D1 = D_s[qc + 1];
+                const float p0 = ex2(s[0] - L0), p1 = ex2(s[1] - L1), p2 = ex2(s[2] - L0), p3 = ex2(s[3] - L1);   // 0 on padding (L=+inf)
+                const float pa[4] = {tf32r(p0), tf32r(p2), tf32r(p1), tf32r(p3)};
+                const float da[4] = {tf32r(p0 * (dp[0] - D0)), tf32r(p2 * (dp[2] - D0)), tf32r(p1 * (dp[1] - D1)), tf32r(p3 * (dp[3] - D1))};
+                float g0[HD / 8], g1[HD / 8], q0v[HD / 8], q1v[HD / 8];
+                lds_half<HD>(g0, Bs + (qq + 2 * t) * LD + g * (HD / 8));
+                lds_half<HD>(g1, Bs + (qq + 2 * t + 1) * LD + g * (HD / 8));
+                lds_half<HD>(q0v, As + (qq + 2 * t) * LD + g * (HD / 8));
+                lds_half<HD>(q1v, As + (qq + 2 * t + 1) * LD + g * (HD / 8));
 #pragma unroll
-                for (int j = 0; j < NT; ++j) {
-                    const int qc = qb + j * 8 + 2 * t;
-                    const float2 L01 = *reinterpret_cast<const float2*>(lse_s + qc), D01 = *reinterpret_cast<const float2*>(D_s + qc);
-                    const float p0 = ex2(s[j][0] - L01.x), p1 = ex2(s[j][1] - L01.y), p2 = ex2(s[j][2] - L01.x), p3 = ex2(s[j][3] - L01.y);   // 0 on padding
-                    const float pa[4] = {tf32r(p0), tf32r(p2), tf32r(p1), tf32r(p3)};
-                    const float da[4] = {tf32r(p0 * (dp[j][0] - D01.x)), tf32r(p2 * (dp[j][2] - D01.x)), tf32r(p1 * (dp[j][1] - D01.y)),
-                                         tf32r(p3 * (dp[j][3] - D01.y))};
-                    float g0[HD / 8], g1[HD / 8], q0v[HD / 8], q1v[HD / 8];
-                    lds_half<HD>(g0, Bs + (qc) * LD + g * (HD / 8));
-                    lds_half<HD>(g1, Bs + (qc + 1) * LD + g * (HD / 8));
-                    lds_half<HD>(q0v, As + (qc) * LD + g * (HD / 8));
-                    lds_half<HD>(q1v, As + (qc + 1) * LD + g * (HD / 8));
-#pragma unroll
-                    for (int nt = 0; nt < HD / 8; ++nt) {
-                        mma_tf32(dv[nt], pa, g0[nt], g1[nt]);
-                        mma_tf32(dk[nt], da, q0v[nt], q1v[nt]);
-                    }
+                for (int nt = 0; nt < HD / 8; ++nt) {
+                    mma_tf32(dv[nt], pa, g0[nt], g1[nt]);
+                    mma_tf32(dk[nt], da, q0v[nt], q1v[nt]);
                 }
             }
         }

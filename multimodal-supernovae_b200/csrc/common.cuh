@@ -186,7 +186,9 @@ int launch_ffn_fused_fwd(const float* X, const float* W1, const float* b1, const
 int launch_ffn_fused_bwd(const float* dY, const float* xhat, const float* rstd, const float* X, const float* W1, const float* b1,
                          const float* W2, const float* gamma, float* dX, const int32_t* n_rows_dev, int M_cap, int E, const DropCfg& drop,
                          float* partial, size_t pstride, size_t o_w1, size_t o_b1, size_t o_w2, size_t o_b2, size_t o_g, size_t o_b,
-                         cudaStream_t st);
+                         float* partial2, cudaStream_t st);
+size_t ffn_fused_slab_floats(int E);        // one FFN-only slab of the second slab set (w1 | b1 | w2 | b2 | gamma | beta)
+int ffn_fused_bwd_slab_sets(int E);         // 2 when the backward of this width runs two CTAs per SM
 int launch_embed_fwd(const float* x, const float* t, const int32_t* cu_seqlens, const int32_t* tok_src, const float* div_term,
                      const float* w, const float* b, const float* band_emb, int B, int T, int E, int nband, float* out,
                      cudaStream_t st, const DropCfg& drop);

@@ -163,6 +163,87 @@ __global__ void __launch_bounds__(256) gelu_stats_kernel(const float* __restrict
         stat_part[(size_t)blockIdx.x * 2 * dim + i] = s;
     }
 }
+// Same pass, vectorised: TPR = dim/4 threads per row (one float4 each), 256/TPR rows per CTA pass, 4 passes in flight per thread
+// (the scalar version above keeps ONE 128-byte load in flight per warp: ~20 us of pure latency for a 4.7 MB map).
+template <int TPR>
+__global__ void __launch_bounds__(256) gelu_stats_vec_kernel(const float* __restrict__ u, float* __restrict__ a, int R, double* __restrict__ stat_part) {
+    constexpr int DIM = 4 * TPR, RPP = 256 / TPR, U = 4;
+    __shared__ double red[2][RPP][DIM];
+    const int c4 = (threadIdx.x % TPR) * 4, rl = threadIdx.x / TPR;
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r0 = blockIdx.x * RPP + rl; r0 < R; r0 += gridDim.x * RPP * U) {
+        float4 v[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int r = r0 + k * gridDim.x * RPP;
+            v[k] = r < R ? __ldg(reinterpret_cast<const float4*>(u + (size_t)r * DIM + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int r = r0 + k * gridDim.x * RPP;
+            if (r >= R) break;
+            const float4 g = make_float4(gelu_erf(v[k].x), gelu_erf(v[k].y), gelu_erf(v[k].z), gelu_erf(v[k].w));
+            *reinterpret_cast<float4*>(a + (size_t)r * DIM + c4) = g;
+            s1[0] += g.x; s1[1] += g.y; s1[2] += g.z; s1[3] += g.w;
+            s2[0] = fmaf(g.x, g.x, s2[0]); s2[1] = fmaf(g.y, g.y, s2[1]); s2[2] = fmaf(g.z, g.z, s2[2]); s2[3] = fmaf(g.w, g.w, s2[3]);
+        }
+    }
+    if (!stat_part) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { red[0][rl][c4 + j] = (double)s1[j]; red[1][rl][c4 + j] = (double)s2[j]; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * DIM; i += 256) {
+        const int sec = i / DIM, c = i % DIM;
+        double s = 0.0;
+#pragma unroll 8
+        for (int w = 0; w < RPP; ++w) s += red[sec][w][c];
+        stat_part[(size_t)blockIdx.x * 2 * DIM + i] = s;
+    }
+}
+template <int TPR>
+__global__ void __launch_bounds__(256) bn_bwd_stats_vec_kernel(const float* __restrict__ dout, const float* __restrict__ a, const float* __restrict__ mean,
+                                                               const float* __restrict__ rstd, int R, double* __restrict__ stat_part, const DropCfg drop) {
+    constexpr int DIM = 4 * TPR, RPP = 256 / TPR, U = 4;
+    __shared__ double red[2][RPP][DIM];
+    const int c4 = (threadIdx.x % TPR) * 4, rl = threadIdx.x / TPR;
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c4), rs = *reinterpret_cast<const float4*>(rstd + c4);
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r0 = blockIdx.x * RPP + rl; r0 < R; r0 += gridDim.x * RPP * U) {
+        float4 g[U], av[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int r = r0 + k * gridDim.x * RPP;
+            g[k] = av[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < R) {
+                g[k] = __ldg(reinterpret_cast<const float4*>(dout + (size_t)r * DIM + c4));
+                av[k] = __ldg(reinterpret_cast<const float4*>(a + (size_t)r * DIM + c4));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int r = r0 + k * gridDim.x * RPP;
+            if (r >= R) break;
+            if (drop.thresh) {                                                     // dout is the gradient AFTER this BN's dropout
+                const uint32_t rk = drop_rowkey(drop, (uint32_t)r);
+                g[k].x *= drop_scale(drop, rk, (uint32_t)c4); g[k].y *= drop_scale(drop, rk, (uint32_t)c4 + 1);
+                g[k].z *= drop_scale(drop, rk, (uint32_t)c4 + 2); g[k].w *= drop_scale(drop, rk, (uint32_t)c4 + 3);
+            }
+            s1[0] += g[k].x; s1[1] += g[k].y; s1[2] += g[k].z; s1[3] += g[k].w;
+            s2[0] = fmaf(g[k].x, (av[k].x - mu.x) * rs.x, s2[0]); s2[1] = fmaf(g[k].y, (av[k].y - mu.y) * rs.y, s2[1]);
+            s2[2] = fmaf(g[k].z, (av[k].z - mu.z) * rs.z, s2[2]); s2[3] = fmaf(g[k].w, (av[k].w - mu.w) * rs.w, s2[3]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { red[0][rl][c4 + j] = (double)s1[j]; red[1][rl][c4 + j] = (double)s2[j]; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * DIM; i += 256) {
+        const int sec = i / DIM, c = i % DIM;
+        double s = 0.0;
+#pragma unroll 8
+        for (int w = 0; w < RPP; ++w) s += red[sec][w][c];
+        stat_part[(size_t)blockIdx.x * 2 * DIM + i] = s;
+    }
+}
 // stats[i] = sum over CTAs (one warp per output, fixed lane/shuffle order -> deterministic)
 __device__ __forceinline__ double warp_sum_f64(double v) {
 #pragma unroll
@@ -238,6 +319,50 @@ __global__ void dwconv_kernel(const float* __restrict__ x, const float* __restri
         }
         if (addend) acc += addend[i];
         y[i] = acc;
+    }
+}
+// Same convolution, one sample at a time per CTA: the [P, dim] map (4.6 KB at 6x6x32) is staged in shared memory with coalesced
+// float4 loads and the thread's k*k taps of its channel live in registers, so the 25 reads per output hit shared memory instead
+// of 25 scattered global loads.  dim == 32, k <= 5, P <= 64.
+template <int K>
+__global__ void __launch_bounds__(256) dwconv_smem_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                          const float* __restrict__ addend, float* __restrict__ y, int B, int Hp, int Wp,
+                                                          int transposed) {
+    constexpr int DIM = 32, MAXP = 64, MAXKK = K * K, k = K, h = K / 2, kk = K * K;
+    __shared__ __align__(16) float sx[2][MAXP * DIM];
+    const int P = Hp * Wp, n = P * DIM;
+    const int c = threadIdx.x % DIM, pg = threadIdx.x / DIM;          // channel, position group (8 groups)
+    float wt[MAXKK];
+#pragma unroll
+    for (int i = 0; i < MAXKK; ++i) {
+        // transposed (input gradient): tap (ii, jj) reads x[p - (ii-h, jj-h)] = correlation with the flipped kernel
+        const int src = transposed ? (kk - 1 - i) : i;
+        wt[i] = i < kk ? __ldg(w + c * kk + src) : 0.f;
+    }
+    const float bv = bias ? __ldg(bias + c) : 0.f;
+    int buf = 0;
+    for (int b = blockIdx.x; b < B; b += gridDim.x, buf ^= 1) {
+        const float* xb = x + (size_t)b * n;
+        for (int i = threadIdx.x * 4; i < n; i += 256 * 4) *reinterpret_cast<float4*>(&sx[buf][i]) = __ldg(reinterpret_cast<const float4*>(xb + i));
+        __syncthreads();                                             // double buffered: one barrier per sample
+        for (int p = pg; p < P; p += 256 / DIM) {
+            const int py = p / Wp, px = p % Wp;
+            float acc = bv;
+#pragma unroll
+            for (int ii = 0; ii < K; ++ii) {
+                const int yy = py + ii - h;
+                if (yy < 0 || yy >= Hp) continue;
+#pragma unroll
+                for (int jj = 0; jj < K; ++jj) {
+                    const int xx = px + jj - h;
+                    if (xx < 0 || xx >= Wp) continue;
+                    acc = fmaf(sx[buf][(yy * Wp + xx) * DIM + c], wt[ii * k + jj], acc);
+                }
+            }
+            const size_t o = (size_t)b * n + (size_t)p * DIM + c;
+            if (addend) acc += __ldg(addend + o);
+            y[o] = acc;
+        }
     }
 }
 // depthwise weight/bias gradient partials: partial[cta][woff + c*k*k + tap] = sum du[r,c]*x[r+tap,c], [boff + c] = sum du.
@@ -389,9 +514,33 @@ __global__ void gelu_pair_kernel(const float* __restrict__ u, float* __restrict_
     }
 }
 
+// dispatchers: vectorised / shared-memory variants for the shapes of the shipped configurations, general kernels otherwise
+inline void launch_gelu_stats(const float* u, float* a, int R, int dim, double* stat_part, cudaStream_t st) {
+    if (dim == 32 && aligned16(u) && aligned16(a)) gelu_stats_vec_kernel<8><<<kSlabs, 256, 0, st>>>(u, a, R, stat_part);
+    else if (dim == 64 && aligned16(u) && aligned16(a)) gelu_stats_vec_kernel<16><<<kSlabs, 256, 0, st>>>(u, a, R, stat_part);
+    else gelu_stats_kernel<<<kSlabs, 256, 0, st>>>(u, a, R, dim, stat_part);
+}
+inline void launch_bn_bwd_stats(const float* dout, const float* a, const float* mean, const float* rstd, int R, int dim, double* stat_part,
+                                const DropCfg& drop, cudaStream_t st) {
+    if (dim == 32 && aligned16(dout) && aligned16(a)) bn_bwd_stats_vec_kernel<8><<<kSlabs, 256, 0, st>>>(dout, a, mean, rstd, R, stat_part, drop);
+    else if (dim == 64 && aligned16(dout) && aligned16(a)) bn_bwd_stats_vec_kernel<16><<<kSlabs, 256, 0, st>>>(dout, a, mean, rstd, R, stat_part, drop);
+    else bn_bwd_stats_kernel<<<kSlabs, 256, 0, st>>>(dout, a, mean, rstd, R, dim, stat_part, drop);
+}
+inline int ew_blocks(size_t n);
+inline void launch_dwconv(const float* x, const float* w, const float* bias, const float* addend, float* y, int B, int Hp, int Wp, int dim, int k,
+                          int transposed, cudaStream_t st) {
+    const int grid = B < 4 * kSlabs ? B : 4 * kSlabs;
+    if (dim == 32 && Hp * Wp <= 64 && k == 5 && aligned16(x)) dwconv_smem_kernel<5><<<grid, 256, 0, st>>>(x, w, bias, addend, y, B, Hp, Wp, transposed);
+    else if (dim == 32 && Hp * Wp <= 64 && k == 3 && aligned16(x)) dwconv_smem_kernel<3><<<grid, 256, 0, st>>>(x, w, bias, addend, y, B, Hp, Wp, transposed);
+    else dwconv_kernel<<<ew_blocks((size_t)B * Hp * Wp * dim), 256, (size_t)k * k * dim * 4, st>>>(x, w, bias, addend, y, B, Hp, Wp, dim, k, transposed);
+}
 inline int ew_blocks(size_t n) { size_t b = (n + 255) / 256; return (int)(b < 4096 ? (b ? b : 1) : 4096); }
 
 }  // namespace
+// convmixer_tc.cu: patch embedding as an implicit GEMM on tensor cores (prec >= 1)
+bool patch_conv_tc_supported(const mvn_conv_cfg& c);
+int launch_patch_conv_fwd_tc(const mvn_conv_cfg& c, const float* img, const float* Wt, float* u, float* a, double* stat_part, cudaStream_t st);
+int launch_patch_conv_wgrad_tc(const mvn_conv_cfg& c, const float* img, const float* dU, float* partial, size_t pstride, size_t woff, cudaStream_t st);
 }  // namespace mvn
 
 using namespace mvn;
@@ -431,7 +580,7 @@ extern "C" int mvn_convmixer_fwd_stage(const mvn_conv_cfg* cfg, int stage, const
     };
     auto gelu_stats = [&](int s) -> int {
         const ConvWs::Bn bn = w.bn(s);
-        gelu_stats_kernel<<<kSlabs, 256, 0, st>>>(bn.u, bn.a, R, dim, c.training ? w.stat_part : nullptr);
+        launch_gelu_stats(bn.u, bn.a, R, dim, c.training ? w.stat_part : nullptr, st);
         MVN_LAUNCH_CHECK();
         if (c.training) {
             stat_reduce_kernel<<<cdiv(2 * dim, 8), 256, 0, st>>>(w.stat_part, kSlabs, 2 * dim, bn_stats + (size_t)s * 2 * dim);
@@ -440,6 +589,16 @@ extern "C" int mvn_convmixer_fwd_stage(const mvn_conv_cfg* cfg, int stage, const
         return 0;
     };
 
+    if (stage == 0 && c.prec >= 1 && patch_conv_tc_supported(c)) {
+        // implicit GEMM from the image, GELU and the BatchNorm partial sums in the epilogue: one pass over 43.2 KB per sample
+        const ConvWs::Bn bn = w.bn(0);
+        MVN_TRY(launch_patch_conv_fwd_tc(c, img, params + o.patch_w, bn.u, bn.a, c.training ? w.stat_part : nullptr, st));
+        if (c.training) {
+            stat_reduce_kernel<<<cdiv(2 * dim, 8), 256, 0, st>>>(w.stat_part, kSlabs, 2 * dim, bn_stats);
+            MVN_LAUNCH_CHECK();
+        }
+        return 0;
+    }
     if (stage == 0) {
         im2col_kernel<<<ew_blocks((size_t)R * Kp), 256, 0, st>>>(img, w.col, c.B, c.C, c.H, c.W, c.patch_size);
         MVN_LAUNCH_CHECK();
@@ -453,13 +612,12 @@ extern "C" int mvn_convmixer_fwd_stage(const mvn_conv_cfg* cfg, int stage, const
         const float* LP = params + o.layer0 + (size_t)d * o.layer_stride;
         const float* xin = w.bn(stage - 1).z;
         if (stage & 1) {        // depthwise conv of layer d on z_{2d}
-            dwconv_kernel<<<ew_blocks(n), 256, (size_t)c.kernel_size * c.kernel_size * dim * 4, st>>>(xin, LP + o.dw_w, LP + o.dw_b, nullptr, w.bn(stage).u,
-                                                                                                     c.B, Hp, Wp, dim, c.kernel_size, 0);
+            launch_dwconv(xin, LP + o.dw_w, LP + o.dw_b, nullptr, w.bn(stage).u, c.B, Hp, Wp, dim, c.kernel_size, 0, st);
             MVN_LAUNCH_CHECK();
         } else {                // pointwise conv on y = BN_A(...) + x
             GemmEpilogue e;
             e.bias = LP + o.pw_b;
-            MVN_TRY(launch_gemm(xin, LP + o.pw_w, w.bn(stage).u, nullptr, R, dim, dim, true, e, 0, st));
+            MVN_TRY(launch_gemm(xin, LP + o.pw_w, w.bn(stage).u, nullptr, R, dim, dim, true, e, c.prec >= 1 ? 1 : 0, st));
         }
         return gelu_stats(stage);
     }
@@ -494,7 +652,7 @@ extern "C" int mvn_convmixer_fwd_stage(const mvn_conv_cfg* cfg, int stage, const
 extern "C" int mvn_convmixer_bwd_stage(const mvn_conv_cfg* cfg, int stage, const float* params, const float* img, const double* bn_stats,
                                        double* bn_stats_bwd, const float* dout, float* grads, void* workspace, size_t workspace_bytes,
                                        void* stream) {
-    (void)img; (void)bn_stats;
+    (void)bn_stats;
     MVN_TRY(conv_check(cfg));
     const mvn_conv_cfg& c = *cfg;
     const int nbn = 1 + 2 * c.depth;
@@ -518,7 +676,7 @@ extern "C" int mvn_convmixer_bwd_stage(const mvn_conv_cfg* cfg, int stage, const
         size_t g, b;
         bn_param(o, s, &g, &b);
         const ConvWs::Bn bn = w.bn(s);
-        bn_bwd_stats_kernel<<<kSlabs, 256, 0, st>>>(w.dZ, bn.a, bn.mean, bn.rstd, R, dim, w.stat_part, conv_drop(c, s));
+        launch_bn_bwd_stats(w.dZ, bn.a, bn.mean, bn.rstd, R, dim, w.stat_part, conv_drop(c, s), st);
         MVN_LAUNCH_CHECK();
         bn_bwd_reduce_kernel<<<cdiv(2 * dim, 8), 256, 0, st>>>(w.stat_part, kSlabs, dim, bn_stats_bwd + (size_t)s * 2 * dim, grads + g, grads + b);
         MVN_LAUNCH_CHECK();
@@ -563,6 +721,11 @@ extern "C" int mvn_convmixer_bwd_stage(const mvn_conv_cfg* cfg, int stage, const
         bn_bwd_eval_kernel<<<ew_blocks(n), 256, 0, st>>>(w.dZ, bn.u, bn.scale, n, dim, w.dU);
     }
     MVN_LAUNCH_CHECK();
+    if (s == 0 && c.prec >= 1 && patch_conv_tc_supported(c)) {
+        MVN_CHECK_ARG(img != nullptr, "convmixer_bwd_stage: img is null at stage 0");
+        MVN_TRY(launch_patch_conv_wgrad_tc(c, img, w.dU, part, ps, o.patch_w, st));
+        return launch_reduce_partials(part + o.patch_w, ps, (size_t)dim * Kp, grads + o.patch_w, 0, st);
+    }
     if (s == 0) {
         MVN_TRY(launch_wgrad_partials(w.dU, w.col, nullptr, R, dim, Kp, part, ps, o.patch_w, -1, 0, st));
         return launch_reduce_partials(part + o.patch_w, ps, (size_t)dim * Kp, grads + o.patch_w, 0, st);
@@ -573,14 +736,14 @@ extern "C" int mvn_convmixer_bwd_stage(const mvn_conv_cfg* cfg, int stage, const
     if (s & 1) {    // depthwise conv: input x = z_{s-1}; total grad of x = dYres (residual path) + dwconv^T(dU)
         dwconv_wgrad_kernel<<<kSlabs, 256, (size_t)2 * P * dim * sizeof(float), st>>>(w.dU, w.bn(s - 1).z, c.B, Hp, Wp, dim, c.kernel_size, part, ps, lbase + o.dw_w, lbase + o.dw_b);
         MVN_LAUNCH_CHECK();
-        dwconv_kernel<<<ew_blocks(n), 256, (size_t)c.kernel_size * c.kernel_size * dim * 4, st>>>(w.dU, LP + o.dw_w, nullptr, w.dYres, w.dZ, c.B, Hp, Wp, dim,
-                                                                                                 c.kernel_size, 1);
+        launch_dwconv(w.dU, LP + o.dw_w, nullptr, w.dYres, w.dZ, c.B, Hp, Wp, dim, c.kernel_size, 1, st);
         MVN_LAUNCH_CHECK();
         MVN_TRY(launch_reduce_partials(part + lbase + o.dw_w, ps, (size_t)dim * c.kernel_size * c.kernel_size + dim, grads + lbase + o.dw_w, 0, st));
     } else {        // pointwise conv: input y = z_{s-1} (BN_A output + residual); dy feeds BN_A and the residual path
-        MVN_TRY(launch_wgrad_partials(w.dU, w.bn(s - 1).z, nullptr, R, dim, dim, part, ps, lbase + o.pw_w, (long long)(lbase + o.pw_b), 0, st));
+        const int gp = c.prec >= 1 ? 1 : 0;
+        MVN_TRY(launch_wgrad_partials(w.dU, w.bn(s - 1).z, nullptr, R, dim, dim, part, ps, lbase + o.pw_w, (long long)(lbase + o.pw_b), gp, st));
         GemmEpilogue e0;
-        MVN_TRY(launch_gemm(w.dU, LP + o.pw_w, w.dZ, nullptr, R, dim, dim, false, e0, 0, st));
+        MVN_TRY(launch_gemm(w.dU, LP + o.pw_w, w.dZ, nullptr, R, dim, dim, false, e0, gp, st));
         MVN_CUDA(cudaMemcpyAsync(w.dYres, w.dZ, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
         MVN_TRY(launch_reduce_partials(part + lbase + o.pw_w, ps, (size_t)dim * dim + dim, grads + lbase + o.pw_w, 0, st));
     }

@@ -54,6 +54,7 @@ struct Workspace {
     float *pooled, *p1, *p2, *ynorm, *norm; int32_t* argmax;
     float *dX, *dA, *dz, *dqkv, *dh, *d_p2, *d_p1, *d_pooled;
     float* partial; size_t pstride;
+    float* partial2;        // second (FFN-only) slab set of the fused backward, when it runs two CTAs per SM
     char* layer_base; size_t layer_bytes;
     size_t bytes;
     size_t M, E, F, H;
@@ -103,6 +104,7 @@ Workspace carve(const mvn_seq_cfg& c, void* base) {
     if (head > w.pstride) w.pstride = head;
     if (emb > w.pstride) w.pstride = emb;
     w.partial = (float*)take((size_t)kSlabs * w.pstride * 4);
+    w.partial2 = (w.fuse_ffn && ffn_fused_bwd_slab_sets(c.E) == 2) ? (float*)take((size_t)kSlabs * ffn_fused_slab_floats(c.E) * 4) : nullptr;
     // per-layer saved activations
     {
         size_t lb = 0;
@@ -269,7 +271,7 @@ extern "C" int mvn_seq_encoder_bwd(const mvn_seq_cfg* cfg, const float* params, 
         if (fuse_ffn) {
             // norm2 backward + ff.2 / ff.0 input and weight gradients in one kernel; h is recomputed from x1 on chip
             MVN_TRY(launch_ffn_fused_bwd(w.dX, lb.xhat2, lb.rstd2, lb.x1, P + o.w1, P + o.b1, P + o.w2, P + o.g2, w.dA, nrows, M, E,
-                                         make_drop(c.dropout_p, c.seed, 2 + 2 * l), part, ps, o.w1, o.b1, o.w2, o.b2, o.g2, o.b2n, st));
+                                         make_drop(c.dropout_p, c.seed, 2 + 2 * l), part, ps, o.w1, o.b1, o.w2, o.b2, o.g2, o.b2n, w.partial2, st));
         } else {
         // norm2 backward: dX (grad of x2) -> dz2 in w.dz
         MVN_TRY(launch_ln_bwd(w.dX, lb.xhat2, lb.rstd2, P + o.g2, w.dz, nrows, M, E, part, ps, o.g2, o.b2n, st, make_drop(c.dropout_p, c.seed, 2 + 2 * l)));
@@ -297,6 +299,9 @@ extern "C" int mvn_seq_encoder_bwd(const mvn_seq_cfg* cfg, const float* params, 
         e3.addend = w.dz;
         MVN_TRY(launch_gemm(w.dqkv, P + o.wqkv, w.dX, nrows, M, E, 3 * E, false, e3, gp, st));
         MVN_TRY(launch_reduce_partials(part, ps, o.layer_stride, grads + o.layer0 + (size_t)l * o.layer_stride, 0, st));
+        if (fuse_ffn && w.partial2)       // the second slab set holds the feed-forward gradients of the CTAs >= kSlabs
+            MVN_TRY(launch_reduce_partials(w.partial2, ffn_fused_slab_floats(E), ffn_fused_slab_floats(E),
+                                           grads + o.layer0 + (size_t)l * o.layer_stride + o.w1, 1, st));
     }
     // embedding_mag / band_emb
     MVN_TRY(launch_embed_bwd_partials(x, w.tok_src, w.dX, nrows, M, c.T, E, c.nband, part, ps, 0, st, make_drop(c.dropout_p, c.seed, 0)));

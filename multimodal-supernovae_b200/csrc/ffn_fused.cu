@@ -46,7 +46,7 @@ __device__ __forceinline__ float quad_sum(float v) {
 // Shared-memory geometry.  Row strides are chosen so that every fragment load is bank-conflict free:
 //   W1s [F][E+4]  : read as B with rows = n = g, cols = k = t  (4g + t)   and with rows = k = 2t, cols = n = g  (8t + g)
 //   W2s [E][F+8]  : read as B with rows = n = g, 64-bit at col 2t (8g + 2t per half warp) and with rows = k = t, cols = g (8t + g)
-template <int E>
+template <int E, int THREADS = 512>
 struct FfnGeom {
     static constexpr int F = 4 * E;
     static constexpr int P1 = E + 4;
@@ -54,7 +54,7 @@ struct FfnGeom {
     static constexpr int W_FLOATS = F * P1 + E * P2;
     static constexpr int VEC_FLOATS = F + 3 * E;                    // b1 | b2 | gamma | beta
     // backward token tile
-    static constexpr int TT = (E == 64) ? 32 : 64;                  // tokens per tile: FF_THREADS * 4 / E
+    static constexpr int TT = THREADS * 4 / E;                      // tokens per tile: one float4 per thread in the LayerNorm-backward phase
     static constexpr int PX = E + 8;                                // dz / x1 tiles: B-fragment reads (rows = t): 8t + g
     static constexpr int PH = F + 8;                                // h tile: A-fragment reads in the weight phase (rows = t)
     static constexpr int PD = F + 8;                                // dh tile: 64-bit A-fragment reads of the dx GEMM (rows = g, col 2t) and rows = t reads
@@ -229,6 +229,7 @@ struct FfnBwdArgs {
     int M_cap;
     DropCfg drop;
     float* partial; size_t pstride;                 // slab s = blockIdx.x at partial + s * pstride
+    float* partial2; size_t pstride2;               // CTAs >= kSlabs (two-CTA-per-SM launch): FFN-only slabs, offsets relative to o_w1
     size_t o_w1, o_b1, o_w2, o_b2, o_g, o_b;        // float offsets inside a slab
 };
 
@@ -240,15 +241,20 @@ struct FfnBwdArgs {
 //                     (ii) its 16 hidden rows of dW2^T += h^T dz and dW1 += dh^T x1 (contraction over the tile's tokens),
 //                     accumulators live in registers for the CTA's whole token range; db1 comes from the A fragments.
 // The CTA finally writes one slab of partial sums (deterministic fixed-order reduction by launch_reduce_partials).
-template <int E>
-__global__ void __launch_bounds__(FF_THREADS, 1) ffn_bwd_kernel(const FfnBwdArgs a) {
-    using G = FfnGeom<E>;
+// WARPS = 16: one CTA per SM (E = 64 needs 225 KB of shared memory).  WARPS = 8 (E = 32, 81 KB): two CTAs per SM, so one CTA's
+// load / barrier bubbles are filled by the other's MMAs; CTAs >= kSlabs write their partial sums to the second slab set.
+template <int E, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) ffn_bwd_kernel(const FfnBwdArgs a) {
+    constexpr int FF_WARPS = WARPS, FF_THREADS = WARPS * 32;
+    using G = FfnGeom<E, FF_THREADS>;
     constexpr int F = G::F, KS = E / 8, NT = E / 8, P1 = G::P1, P2 = G::P2, TT = G::TT, PX = G::PX, PH = G::PH, PD = G::PD;
     constexpr int RB = TT / 16, FR = FF_WARPS / RB, CPW = (F / 8) / FR;          // row blocks, hidden ranges, 8-col chunks per warp
     constexpr int LPR = E / 4;                                                    // lanes per row in P0 (float4 each)
-    constexpr int NACC = (E == 64) ? 2 : 1;                                       // weight-gradient kinds per warp
+    constexpr int MTILES = F / 16;                                                // 16-row tiles of the weight gradients
+    constexpr int NACC = 2 * MTILES / FF_WARPS;                                   // weight-gradient kinds per warp (2: both, 1: one of them)
     static_assert(FF_THREADS / LPR == TT, "P0 covers the tile in one pass");
     static_assert(RB * NT == FF_WARPS, "one dx tile per warp");
+    static_assert(NACC == 1 || NACC == 2, "weight-gradient tiles must divide over the warps");
     extern __shared__ __align__(16) float smem_f[];
     float* W1s = smem_f;
     float* W2s = W1s + F * P1;
@@ -275,8 +281,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_bwd_kernel(const FfnBwdArgs
     const int rb = warp / FR, fr = warp % FR;
     // PB ownership: dx tile (rows xrb*16.., cols xnt*8..) ; weight rows f0 .. f0+15
     const int xrb = warp / NT, xnt = warp % NT;
-    const int wkind = (E == 64) ? 0 : warp / 8;                   // E == 32: warps 0-7 own dW2^T, warps 8-15 own dW1
-    const int f0 = ((E == 64) ? warp : (warp & 7)) * 16;
+    const int wkind = (NACC == 2) ? 0 : warp / MTILES;            // NACC == 1: the first MTILES warps own dW2^T, the others dW1
+    const int f0 = ((NACC == 2) ? warp : (warp % MTILES)) * 16;
     float acc[NACC][NT][4];
 #pragma unroll
     for (int k = 0; k < NACC; ++k)
@@ -373,12 +379,12 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_bwd_kernel(const FfnBwdArgs
 #pragma unroll 2
         for (int ks = 0; ks < TT / 8; ++ks) {
             const int k_lo = 8 * ks + t, k_hi = k_lo + 4;
-            if (E == 64 || wkind == 0) {                                        // dW2^T[f, e] += h[tok, f] dz[tok, e]
+            if (NACC == 2 || wkind == 0) {                                      // dW2^T[f, e] += h[tok, f] dz[tok, e]
                 const float af[4] = {hs[k_lo * PH + f0 + g], hs[k_lo * PH + f0 + g + 8], hs[k_hi * PH + f0 + g], hs[k_hi * PH + f0 + g + 8]};
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) mma_tf32(acc[0][nt], af, dzs[k_lo * PX + 8 * nt + g], dzs[k_hi * PX + 8 * nt + g]);
             }
-            if (E == 64 || wkind == 1) {                                        // dW1[f, e] += dh[tok, f] x1[tok, e]
+            if (NACC == 2 || wkind == 1) {                                      // dW1[f, e] += dh[tok, f] x1[tok, e]
                 const float af[4] = {dhs[k_lo * PD + f0 + g], dhs[k_lo * PD + f0 + g + 8], dhs[k_hi * PD + f0 + g], dhs[k_hi * PD + f0 + g + 8]};
                 db1_lo += af[0] + af[2]; db1_hi += af[1] + af[3];
 #pragma unroll
@@ -389,22 +395,25 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ffn_bwd_kernel(const FfnBwdArgs
     }
 
     // ---- slab write -------------------------------------------------------------------------------------------------
-    float* slab = a.partial + (size_t)blockIdx.x * a.pstride;
+    // slab of this CTA: the first kSlabs CTAs use the caller's per-layer slabs, the others the second (FFN-only) slab set, whose
+    // offsets are relative to o_w1
+    float* slab = (int)blockIdx.x < kSlabs ? a.partial + (size_t)blockIdx.x * a.pstride
+                                           : a.partial2 + (size_t)(blockIdx.x - kSlabs) * a.pstride2 - a.o_w1;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
         const int e = 8 * nt + 2 * t;
-        if (E == 64 || wkind == 0) {                                            // dW2 is [E][F]: transpose on the way out
+        if (NACC == 2 || wkind == 0) {                                          // dW2 is [E][F]: transpose on the way out
             float* p = slab + a.o_w2;
             p[(size_t)e * F + f0 + g] = acc[0][nt][0]; p[(size_t)(e + 1) * F + f0 + g] = acc[0][nt][1];
             p[(size_t)e * F + f0 + g + 8] = acc[0][nt][2]; p[(size_t)(e + 1) * F + f0 + g + 8] = acc[0][nt][3];
         }
-        if (E == 64 || wkind == 1) {                                            // dW1 is [F][E]
+        if (NACC == 2 || wkind == 1) {                                          // dW1 is [F][E]
             float* p = slab + a.o_w1;
             *reinterpret_cast<float2*>(p + (size_t)(f0 + g) * E + e) = make_float2(acc[NACC - 1][nt][0], acc[NACC - 1][nt][1]);
             *reinterpret_cast<float2*>(p + (size_t)(f0 + g + 8) * E + e) = make_float2(acc[NACC - 1][nt][2], acc[NACC - 1][nt][3]);
         }
     }
-    if (E == 64 || wkind == 1) {
+    if (NACC == 2 || wkind == 1) {
         db1_lo = quad_sum(db1_lo); db1_hi = quad_sum(db1_hi);
         if (t == 0) { slab[a.o_b1 + f0 + g] = db1_lo; slab[a.o_b1 + f0 + g + 8] = db1_hi; }
     }
@@ -445,21 +454,22 @@ int launch_fwd_t(const FfnFwdArgs& a, cudaStream_t st) {
     MVN_LAUNCH_CHECK();
     return 0;
 }
-template <int E>
+template <int E, int WARPS>
 int launch_bwd_t(const FfnBwdArgs& a, cudaStream_t st) {
-    using G = FfnGeom<E>;
+    using G = FfnGeom<E, WARPS * 32>;
     static bool configured = false;
     if (!configured) {
-        MVN_CUDA(cudaFuncSetAttribute(ffn_bwd_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BWD));
+        MVN_CUDA(cudaFuncSetAttribute(ffn_bwd_kernel<E, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BWD));
         configured = true;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(kSlabs); cfg.blockDim = dim3(FF_THREADS); cfg.dynamicSmemBytes = G::SMEM_BWD; cfg.stream = st;     // every slab is written
+    cfg.gridDim = dim3(WARPS == 8 ? 2 * kSlabs : kSlabs);        // every slab is written
+    cfg.blockDim = dim3(WARPS * 32); cfg.dynamicSmemBytes = G::SMEM_BWD; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    MVN_CUDA(cudaLaunchKernelEx(&cfg, ffn_bwd_kernel<E>, a));
+    MVN_CUDA(cudaLaunchKernelEx(&cfg, ffn_bwd_kernel<E, WARPS>, a));
     MVN_LAUNCH_CHECK();
     return 0;
 }
@@ -467,6 +477,13 @@ int launch_bwd_t(const FfnBwdArgs& a, cudaStream_t st) {
 }  // namespace
 
 bool ffn_fused_supported(int E, int ff_mult) { return ff_mult == 4 && (E == 32 || E == 64); }
+// floats of one FFN-only slab (w1 | b1 | w2 | b2 | gamma | beta, the order of the flat parameter layout)
+size_t ffn_fused_slab_floats(int E) { return (size_t)8 * E * E + 4 * E + 3 * E; }
+// number of slab sets the backward writes for this width: 2 when it runs two CTAs per SM
+int ffn_fused_bwd_slab_sets(int E) {
+    static const int v = getenv("MVN_FFN_BWD") ? atoi(getenv("MVN_FFN_BWD")) : 1;     // 0: one 16-warp CTA per SM for every width (A/B measurements)
+    return (E == 32 && v != 0) ? 2 : 1;
+}
 
 int launch_ffn_fused_fwd(const float* X, const float* W1, const float* b1, const float* W2, const float* b2, const float* gamma,
                          const float* beta, float* Y, float* xhat, float* rstd, const int32_t* n_rows_dev, int M_cap, int E, float eps,
@@ -481,14 +498,20 @@ int launch_ffn_fused_fwd(const float* X, const float* W1, const float* b1, const
     a.n_rows_dev = n_rows_dev; a.M_cap = M_cap; a.eps = eps; a.drop = drop;
     static const int variant = getenv("MVN_FFN_FWD") ? atoi(getenv("MVN_FFN_FWD")) : 1;      // 0: one 16-row tile per warp (A/B measurements)
     if (variant == 0) return E == 64 ? launch_fwd_t<64, 1, 16>(a, st) : launch_fwd_t<32, 1, 16>(a, st);
-    return E == 64 ? launch_fwd_t<64, 2, 8>(a, st) : launch_fwd_t<32, 2, 16>(a, st);
+    // measured (scripts/bench_fused.py, C4 token counts): E = 64 is faster with one row tile per warp and 16 warps (73.7 vs 80.9 us),
+    // E = 32 with two row tiles per warp (36.9 vs 38.9 us)
+    if (variant == 2) return E == 64 ? launch_fwd_t<64, 2, 8>(a, st) : launch_fwd_t<32, 2, 16>(a, st);
+    return E == 64 ? launch_fwd_t<64, 1, 16>(a, st) : launch_fwd_t<32, 2, 16>(a, st);
 }
 
 int launch_ffn_fused_bwd(const float* dY, const float* xhat, const float* rstd, const float* X, const float* W1, const float* b1,
                          const float* W2, const float* gamma, float* dX, const int32_t* n_rows_dev, int M_cap, int E, const DropCfg& drop,
                          float* partial, size_t pstride, size_t o_w1, size_t o_b1, size_t o_w2, size_t o_b2, size_t o_g, size_t o_b,
-                         cudaStream_t st) {
+                         float* partial2, cudaStream_t st) {
     MVN_CHECK_ARG(dY && xhat && rstd && X && W1 && W2 && gamma && dX && partial && M_cap > 0, "ffn_fused_bwd: null pointer or empty input");
+    MVN_CHECK_ARG(ffn_fused_bwd_slab_sets(E) == 1 || partial2, "ffn_fused_bwd: the second slab set is missing");
+    MVN_CHECK_ARG(o_b1 == o_w1 + (size_t)4 * E * E && o_w2 == o_b1 + (size_t)4 * E && o_b2 == o_w2 + (size_t)4 * E * E && o_g == o_b2 + E && o_b == o_g + E,
+                  "ffn_fused_bwd: parameter offsets must follow the flat layout w1 | b1 | w2 | b2 | gamma | beta");
     MVN_CHECK_ARG(aligned16(dY) && aligned16(xhat) && aligned16(X) && aligned16(W1) && aligned16(W2) && aligned16(dX) && aligned16(partial) &&
                       pstride % 4 == 0 && o_w1 % 2 == 0,
                   "ffn_fused_bwd: buffers must be 16-byte aligned");
@@ -499,7 +522,9 @@ int launch_ffn_fused_bwd(const float* dY, const float* xhat, const float* rstd, 
     a.dY = dY; a.xhat = xhat; a.rstd = rstd; a.X = X; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.gamma = gamma; a.dX = dX;
     a.n_rows_dev = n_rows_dev; a.M_cap = M_cap; a.drop = drop; a.partial = partial; a.pstride = pstride;
     a.o_w1 = o_w1; a.o_b1 = o_b1; a.o_w2 = o_w2; a.o_b2 = o_b2; a.o_g = o_g; a.o_b = o_b;
-    return E == 64 ? launch_bwd_t<64>(a, st) : launch_bwd_t<32>(a, st);
+    a.partial2 = partial2; a.pstride2 = ffn_fused_slab_floats(E);
+    if (E == 64) return launch_bwd_t<64, 16>(a, st);
+    return ffn_fused_bwd_slab_sets(E) == 2 ? launch_bwd_t<32, 8>(a, st) : launch_bwd_t<32, 16>(a, st);
 }
 
 }  // namespace mvn
@@ -516,7 +541,7 @@ extern "C" int mvn_ffn_fused_fwd(const float* X, const float* W1, const float* b
 
 extern "C" size_t mvn_ffn_fused_bwd_workspace_bytes(int E, int ff_mult) {
     if (!ffn_fused_supported(E, ff_mult)) return 0;
-    return (size_t)kSlabs * (size_t)(8 * E * E + 4 * E + 3 * E) * sizeof(float) + 256;
+    return (size_t)2 * kSlabs * ffn_fused_slab_floats(E) * sizeof(float) + 256;
 }
 
 extern "C" int mvn_ffn_fused_bwd(const float* dY, const float* xhat, const float* rstd, const float* X, const float* W1, const float* b1,
@@ -528,15 +553,17 @@ extern "C" int mvn_ffn_fused_bwd(const float* dY, const float* xhat, const float
     const size_t F = 4 * (size_t)E;
     const size_t o_w1 = 0, o_b1 = F * E, o_w2 = o_b1 + F, o_b2 = o_w2 + E * F, o_g = o_b2 + E, o_b = o_g + E, ps = o_b + E;
     float* part = (float*)align_up((size_t)workspace, 256);
-    if ((char*)part + (size_t)kSlabs * ps * sizeof(float) > (char*)workspace + workspace_bytes) { set_error("ffn_fused_bwd: workspace too small"); return MVN_E_WORKSPACE; }
+    if ((char*)part + (size_t)2 * kSlabs * ps * sizeof(float) > (char*)workspace + workspace_bytes) { set_error("ffn_fused_bwd: workspace too small"); return MVN_E_WORKSPACE; }
+    float* part2 = part + (size_t)kSlabs * ps;
     cudaStream_t st = (cudaStream_t)stream;
     MVN_TRY(launch_ffn_fused_bwd(dY, xhat, rstd, X, W1, b1, W2, gamma, dX, n_rows_dev, M_cap, E, make_drop(dropout_p, seed, (uint32_t)site), part, ps,
-                                 o_w1, o_b1, o_w2, o_b2, o_g, o_b, st));
-    MVN_TRY(launch_reduce_partials(part + o_w1, ps, F * E, dW1, 0, st));
-    MVN_TRY(launch_reduce_partials(part + o_b1, ps, F, db1, 0, st));
-    MVN_TRY(launch_reduce_partials(part + o_w2, ps, E * F, dW2, 0, st));
-    MVN_TRY(launch_reduce_partials(part + o_b2, ps, E, db2, 0, st));
-    MVN_TRY(launch_reduce_partials(part + o_g, ps, E, dgamma, 0, st));
-    MVN_TRY(launch_reduce_partials(part + o_b, ps, E, dbeta, 0, st));
+                                 o_w1, o_b1, o_w2, o_b2, o_g, o_b, part2, st));
+    const int sets = ffn_fused_bwd_slab_sets(E);
+    float* outs[6] = {dW1, db1, dW2, db2, dgamma, dbeta};
+    const size_t offs[6] = {o_w1, o_b1, o_w2, o_b2, o_g, o_b}, lens[6] = {F * E, F, E * F, (size_t)E, (size_t)E, (size_t)E};
+    for (int i = 0; i < 6; ++i) {
+        MVN_TRY(launch_reduce_partials(part + offs[i], ps, lens[i], outs[i], 0, st));
+        if (sets == 2) MVN_TRY(launch_reduce_partials(part2 + offs[i], ps, lens[i], outs[i], 1, st));
+    }
     return 0;
 }

@@ -62,6 +62,11 @@ const CUtensorMap* get_tmap_2d(const float* base, int rows, int cols, int box_ro
     if (it != g_maps.end()) return it->second;
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return nullptr; }
+    // cuTensorMapEncodeTiled is a driver-API call: it needs the primary context bound to THIS thread.  PyTorch's autograd worker
+    // threads only bind it lazily (at their first runtime-API call), so a backward that starts with a tensor-map lookup would get
+    // CUDA_ERROR_INVALID_CONTEXT: one no-op runtime call per thread binds it.
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
     if (g_maps.size() > 4096) {                    // pointers churn (caching allocator): keep the table bounded
         // Descriptors handed out before this call may still be dereferenced by the caller (a launch looks up to four of
         // them before it copies them into the kernel parameters), so a purged generation is only freed at the NEXT purge.

@@ -93,21 +93,32 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const float* __restrict_
                                                         const float* __restrict__ div_term, const float* __restrict__ w,
                                                         const float* __restrict__ bias, const float* __restrict__ band_emb,
                                                         int B, int T, int E, int nband, float* __restrict__ out, const DropCfg drop) {
+    // One lane per (sin, cos) pair: sincosf shares the full-range argument reduction between the two, the pair is stored as one
+    // 64-bit word, and a warp covers 32 / (E/2) tokens per pass (2 tokens at E = 32), so every store instruction writes full lines.
     const int rows = cu[B];
     const int lane = threadIdx.x & 31;
     const int per_band = T / (nband > 0 ? nband : 1);
-    for (int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < rows; m += (gridDim.x * blockDim.x) >> 5) {
+    const int half = E >> 1;
+    const int lpt = half < 32 ? half : 32;                 // lanes per token (E is a power of two >= 16 here)
+    const int tpw = 32 / lpt, sub = lane / lpt, l = lane % lpt;
+    const int nwarp = (gridDim.x * blockDim.x) >> 5;
+    for (int m = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * tpw + sub; m < rows && sub < tpw; m += nwarp * tpw) {
         const int src = tok_src[m];
         const float xv = x[src], tv = t[src];
         const int band = (nband > 1) ? min((src % T) / per_band, nband - 1) : 0;
         const uint32_t rk = drop.thresh ? drop_rowkey(drop, (uint32_t)m) : 0u;
-        for (int e = lane; e < E; e += 32) {
-            const float arg = __fmul_rn(tv, div_term[e >> 1]);
-            const float pe = (e & 1) ? cosf(arg) : sinf(arg);
-            float v = fmaf(xv, w[e], bias[e]) + pe;
-            if (nband > 1) v += band_emb[band * E + e];
-            if (drop.thresh) v *= drop_scale(drop, rk, (uint32_t)e);
-            out[(size_t)m * E + e] = v;
+        for (int i = l; i < half; i += lpt) {
+            const float arg = __fmul_rn(tv, div_term[i]);
+            float sn, cs;
+            sincosf(arg, &sn, &cs);
+            const float2 wv = *reinterpret_cast<const float2*>(w + 2 * i), bv = *reinterpret_cast<const float2*>(bias + 2 * i);
+            float v0 = fmaf(xv, wv.x, bv.x) + sn, v1 = fmaf(xv, wv.y, bv.y) + cs;
+            if (nband > 1) {
+                const float2 be = *reinterpret_cast<const float2*>(band_emb + band * E + 2 * i);
+                v0 += be.x; v1 += be.y;
+            }
+            if (drop.thresh) { v0 *= drop_scale(drop, rk, (uint32_t)(2 * i)); v1 *= drop_scale(drop, rk, (uint32_t)(2 * i + 1)); }
+            *reinterpret_cast<float2*>(out + (size_t)m * E + 2 * i) = make_float2(v0, v1);
         }
     }
 }

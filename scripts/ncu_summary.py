@@ -18,7 +18,8 @@ from collections import defaultdict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "ns ": 1e-3}
-CLASS = [("tc_wgrad", "wgrad"), ("wgrad_kernel", "wgrad"), ("tc_gemm", "gemm"), ("gemm_kernel", "gemm"), ("attn_fwd", "attn_fwd"),
+CLASS = [("ffn_fwd", "fused_fwd"), ("ffn_bwd", "fused_bwd"), ("tc_lse", "loss"), ("tc_grad", "loss"), ("patch_conv", "conv"), ("dwconv", "conv"),
+         ("gelu_stats", "conv"), ("bn_", "conv"), ("tc_wgrad", "wgrad"), ("wgrad_kernel", "wgrad"), ("tc_gemm", "gemm"), ("gemm_kernel", "gemm"), ("attn_fwd", "attn_fwd"),
          ("attn_bwd", "attn_bwd"), ("ln_bwd", "row"), ("reduce_partials", "row"), ("embed", "row"), ("pool", "row"),
          ("lse_dir", "loss"), ("grad_dir", "loss"), ("radam", "optim")]
 COLS = {"dur": "gpu__time_duration.sum", "rd": "dram__bytes_read.sum", "wr": "dram__bytes_write.sum",
@@ -38,6 +39,7 @@ def main():
     ap.add_argument("report")
     ap.add_argument("--tag", required=True)
     ap.add_argument("--precision", default="tf32")
+    ap.add_argument("--head", default="", help="git commit the capture was taken on")
     a = ap.parse_args()
     raw = subprocess.run(["ncu", "-i", a.report, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
@@ -76,6 +78,7 @@ def main():
     for cls, (b, n) in per_class.items():
         t[a.precision][cls] = b / n
     t[a.precision]["_source"] = f"{a.tag}: mean dram__bytes_read.sum + dram__bytes_write.sum per launch, {os.path.basename(a.report)}"
+    t["_source"] = t[a.precision]["_source"] + (f", HEAD {a.head}" if a.head else "")
     json.dump(t, open(tpath, "w"), indent=1, sort_keys=True)
     print("\n".join(lines))
 
