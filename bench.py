@@ -723,7 +723,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=0, help="samples per CPU reference step (0: sized from a probe step so the run ends within a few minutes)")
     ap.add_argument("--dropout", type=float, default=0.00021844858312997214,
                     help="transformer dropout p (default: pretrain_config/maven_pretrain_config.yaml); the CPU reference arm uses 0")
-    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "fused"],
+    ap.add_argument("--precision", default="fused", choices=["fp32", "tf32", "fused"],
                     help="tf32: tcgen05/mma tensor-core tier (fp32 storage, fp32 accumulate; parity 1e-3); fp32: FFMA tier (parity 1e-5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", dest="sweep", action="store_false", help="skip the C5 large-global-batch sweep that follows the headline measurement")

@@ -120,9 +120,8 @@ __device__ __forceinline__ void store_sigma(float* __restrict__ p_lo, float* __r
     }
 }
 // like load_slice, but rows up to the next multiple of 32 are zero-filled (branch-free 32-key blocks)
-template <int HD>
+template <int HD, int LD = HD + 4>
 __device__ __forceinline__ void load_slice32(float* dst, const float* __restrict__ src, size_t ld, int col, int row0, int cnt, float mul) {
-    constexpr int LD = HD + 4;
     const int pad = (cnt + 31) & ~31;
     for (int idx = threadIdx.x; idx < pad * (HD / 4); idx += ATC_THREADS) {
         const int j = idx / (HD / 4), d = (idx % (HD / 4)) * 4;
@@ -137,12 +136,15 @@ __device__ __forceinline__ void load_slice32(float* dst, const float* __restrict
 template <int HD, int NT>
 __device__ __forceinline__ void fwd_block(const float* __restrict__ Ks, const float* __restrict__ Vs, int kb, int kn, const float (*qa)[4],
                                           float (*o)[4], float& m_lo, float& m_hi, float& l_lo, float& l_hi, int g, int t) {
-    constexpr int LD = HD + 4, KS = HD / 8, W = HD / 4;
+    // K is only read in K-form (row g, HD/4 contiguous floats at t*HD/4): an unpadded row stride HD puts the lanes of one
+    // 64- / 128-bit request on disjoint banks (HD+4 made rows 0 and 3 collide at HD = 8: one wavefront in three was a conflict);
+    // V is only read in V-form (rows 2t, 2t+1, HD/8 floats at g*HD/8), conflict-free at HD+4.
+    constexpr int LDK = HD, LD = HD + 4, KS = HD / 8, W = HD / 4;
     float s[NT][4];
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
         float kf[W];
-        lds_vec<HD>(kf, Ks + (kb + j * 8 + g) * LD + t * W);
+        lds_vec<HD>(kf, Ks + (kb + j * 8 + g) * LDK + t * W);
         s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) mma_tf32(s[j], qa[ks], kf[2 * ks], kf[2 * ks + 1]);
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_fwd_mma_kernel(const float* 
             const int k0c = c * CH, kn = min(CH, n - k0c);
             if (nchunks > 1 || rd == 0) {
                 __syncthreads();
-                load_slice32<HD>(Ks, base, ld, E + h * HD, k0c, kn, 1.0f);
+                load_slice32<HD, HD>(Ks, base, ld, E + h * HD, k0c, kn, 1.0f);
                 load_slice32<HD>(Vs, base, ld, 2 * E + h * HD, k0c, kn, 1.0f);
                 __syncthreads();
             }
