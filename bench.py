@@ -595,9 +595,6 @@ def run_gpu(args):
 
     sweep = None
     if args.sweep:
-        if graphed is not None:
-            del graphed
-        del model, opt, resident
         torch.cuda.empty_cache()
         try:
             sweep = c5_sweep(args, world, rank, dev, L)

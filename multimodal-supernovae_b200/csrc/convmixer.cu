@@ -294,6 +294,49 @@ __global__ void bn_apply_kernel(const float* __restrict__ a, const float* __rest
         z[i] = v;
     }
 }
+// float4 variants of the two elementwise BatchNorm passes (dim % 4 == 0, 16-byte aligned maps): a quarter of the threads and memory
+// instructions of the scalar kernels
+__global__ void bn_apply_vec_kernel(const float* __restrict__ a, const float* __restrict__ scale, const float* __restrict__ shift,
+                                    const float* __restrict__ res, float* __restrict__ z, size_t n4, int dim, const DropCfg drop) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t e = i * 4;
+        const int c = (int)(e % dim);
+        const float4 av = __ldg(reinterpret_cast<const float4*>(a) + i);
+        const float4 sc = *reinterpret_cast<const float4*>(scale + c), sh = *reinterpret_cast<const float4*>(shift + c);
+        float4 v = make_float4(fmaf(av.x, sc.x, sh.x), fmaf(av.y, sc.y, sh.y), fmaf(av.z, sc.z, sh.z), fmaf(av.w, sc.w, sh.w));
+        if (drop.thresh) {
+            const uint32_t rk = drop_rowkey(drop, (uint32_t)(e / dim));
+            v.x *= drop_scale(drop, rk, (uint32_t)c); v.y *= drop_scale(drop, rk, (uint32_t)c + 1);
+            v.z *= drop_scale(drop, rk, (uint32_t)c + 2); v.w *= drop_scale(drop, rk, (uint32_t)c + 3);
+        }
+        if (res) { const float4 r = __ldg(reinterpret_cast<const float4*>(res) + i); v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+        reinterpret_cast<float4*>(z)[i] = v;
+    }
+}
+__global__ void bn_bwd_apply_vec_kernel(const float* __restrict__ dout, const float* __restrict__ a, const float* __restrict__ u,
+                                        const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
+                                        const double* __restrict__ stats, double count, size_t n4, int dim, float* __restrict__ du, const DropCfg drop) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t e = i * 4;
+        const int c = (int)(e % dim);
+        const float4 av = __ldg(reinterpret_cast<const float4*>(a) + i), uv = __ldg(reinterpret_cast<const float4*>(u) + i);
+        float4 g = __ldg(reinterpret_cast<const float4*>(dout) + i);
+        if (drop.thresh) {
+            const uint32_t rk = drop_rowkey(drop, (uint32_t)(e / dim));
+            g.x *= drop_scale(drop, rk, (uint32_t)c); g.y *= drop_scale(drop, rk, (uint32_t)c + 1);
+            g.z *= drop_scale(drop, rk, (uint32_t)c + 2); g.w *= drop_scale(drop, rk, (uint32_t)c + 3);
+        }
+        const float avv[4] = {av.x, av.y, av.z, av.w}, uvv[4] = {uv.x, uv.y, uv.z, uv.w}, gv[4] = {g.x, g.y, g.z, g.w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float xh = (avv[j] - mean[c + j]) * rstd[c + j];
+            const float m1 = (float)(stats[c + j] / count), m2 = (float)(stats[dim + c + j] / count);
+            o[j] = scale[c + j] * (gv[j] - m1 - xh * m2) * gelu_erf_grad(uvv[j]);
+        }
+        reinterpret_cast<float4*>(du)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
 // depthwise k x k 'same' convolution, channels-last.  transposed=1 gives the input-gradient (flipped taps) + addend
 __global__ void dwconv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                               const float* __restrict__ addend, float* __restrict__ y, int B, int Hp, int Wp, int dim, int k, int transposed) {
@@ -574,7 +617,10 @@ extern "C" int mvn_convmixer_fwd_stage(const mvn_conv_cfg* cfg, int stage, const
                                                          c.training, running_stats + (size_t)s * 2 * dim, dim, bn.mean, bn.rstd, bn.scale, bn.shift);
         MVN_LAUNCH_CHECK();
         const float* res = (s & 1) ? w.bn(s - 1).z : nullptr;      // "A" BNs sit inside the Residual: add the layer input
-        bn_apply_kernel<<<ew_blocks(n), 256, 0, st>>>(bn.a, bn.scale, bn.shift, res, bn.z, n, dim, conv_drop(c, s));
+        if (dim % 4 == 0 && aligned16(bn.a) && aligned16(bn.z) && (!res || aligned16(res)))
+            bn_apply_vec_kernel<<<ew_blocks(n / 4), 256, 0, st>>>(bn.a, bn.scale, bn.shift, res, bn.z, n / 4, dim, conv_drop(c, s));
+        else
+            bn_apply_kernel<<<ew_blocks(n), 256, 0, st>>>(bn.a, bn.scale, bn.shift, res, bn.z, n, dim, conv_drop(c, s));
         MVN_LAUNCH_CHECK();
         return 0;
     };
@@ -715,8 +761,12 @@ extern "C" int mvn_convmixer_bwd_stage(const mvn_conv_cfg* cfg, int stage, const
     const int s = stage;
     const ConvWs::Bn bn = w.bn(s);
     if (c.training) {
-        bn_bwd_apply_kernel<<<ew_blocks(n), 256, 0, st>>>(w.dZ, bn.a, bn.u, bn.mean, bn.rstd, bn.scale, bn_stats_bwd + (size_t)s * 2 * dim, count, n, dim, w.dU,
-                                                           conv_drop(c, s));
+        if (dim % 4 == 0 && aligned16(w.dZ) && aligned16(bn.a) && aligned16(bn.u) && aligned16(w.dU))
+            bn_bwd_apply_vec_kernel<<<ew_blocks(n / 4), 256, 0, st>>>(w.dZ, bn.a, bn.u, bn.mean, bn.rstd, bn.scale, bn_stats_bwd + (size_t)s * 2 * dim, count,
+                                                                      n / 4, dim, w.dU, conv_drop(c, s));
+        else
+            bn_bwd_apply_kernel<<<ew_blocks(n), 256, 0, st>>>(w.dZ, bn.a, bn.u, bn.mean, bn.rstd, bn.scale, bn_stats_bwd + (size_t)s * 2 * dim, count, n, dim, w.dU,
+                                                              conv_drop(c, s));
     } else {
         bn_bwd_eval_kernel<<<ew_blocks(n), 256, 0, st>>>(w.dZ, bn.u, bn.scale, n, dim, w.dU);
     }

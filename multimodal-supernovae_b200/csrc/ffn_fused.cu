@@ -476,13 +476,21 @@ int launch_bwd_t(const FfnBwdArgs& a, cudaStream_t st) {
 
 }  // namespace
 
+// ffn_fused_tc.cu / gemm_tc.cu
+int launch_ffn_fused_fwd_tc(const float* X, const float* W1, const float* b1, const float* W2, const float* b2, const float* gamma, const float* beta,
+                            float* Y, float* xhat, float* rstd, const int32_t* n_rows_dev, int M_cap, int E, float eps, float wscale, const DropCfg& drop,
+                            cudaStream_t st);
+float tc_trunc_comp();
+
 bool ffn_fused_supported(int E, int ff_mult) { return ff_mult == 4 && (E == 32 || E == 64); }
 // floats of one FFN-only slab (w1 | b1 | w2 | b2 | gamma | beta, the order of the flat parameter layout)
 size_t ffn_fused_slab_floats(int E) { return (size_t)8 * E * E + 4 * E + 3 * E; }
 // number of slab sets the backward writes for this width: 2 when it runs two CTAs per SM
 int ffn_fused_bwd_slab_sets(int E) {
-    static const int v = getenv("MVN_FFN_BWD") ? atoi(getenv("MVN_FFN_BWD")) : 1;     // 0: one 16-warp CTA per SM for every width (A/B measurements)
-    return (E == 32 && v != 0) ? 2 : 1;
+    // MVN_FFN_BWD=2: two 8-warp CTAs per SM at E = 32.  Measured no better than one 16-warp CTA inside the step (fused_bwd 2.32 vs 2.36 ms)
+    // and it doubles the partial-sum slabs to reduce, so the default stays one CTA per SM for every width.
+    static const int v = getenv("MVN_FFN_BWD") ? atoi(getenv("MVN_FFN_BWD")) : 1;
+    return (E == 32 && v == 2) ? 2 : 1;
 }
 
 int launch_ffn_fused_fwd(const float* X, const float* W1, const float* b1, const float* W2, const float* b2, const float* gamma,
@@ -496,7 +504,14 @@ int launch_ffn_fused_fwd(const float* X, const float* W1, const float* b1, const
     FfnFwdArgs a;
     a.X = X; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2; a.gamma = gamma; a.beta = beta; a.Y = Y; a.xhat = xhat; a.rstd = rstd;
     a.n_rows_dev = n_rows_dev; a.M_cap = M_cap; a.eps = eps; a.drop = drop;
-    static const int variant = getenv("MVN_FFN_FWD") ? atoi(getenv("MVN_FFN_FWD")) : 1;      // 0: one 16-row tile per warp (A/B measurements)
+    // MVN_FFN_FWD: -1 (default) per-width choice measured on B200 (scripts/bench_fused.py, C4 token counts): E = 64 -> the tcgen05 kernel
+    // of ffn_fused_tc.cu (73.7 us, the warp-MMA kernel 75.8 us); E = 32 -> the warp-MMA kernel (36.9 us vs 51.2 us: with only four 32-column
+    // chunks per tile the tcgen05 pipeline is all hand-off latency).  3: tcgen05 for both; 1 / 0 / 2: warp-MMA variants (A/B runs).
+    static const int variant = getenv("MVN_FFN_FWD") ? atoi(getenv("MVN_FFN_FWD")) : -1;
+    if ((variant == 3 || (variant == -1 && E == 64)) && aligned16(X) && aligned16(Y) && (!xhat || aligned16(xhat))) {
+        const int r = launch_ffn_fused_fwd_tc(X, W1, b1, W2, b2, gamma, beta, Y, xhat, rstd, n_rows_dev, M_cap, E, eps, tc_trunc_comp(), drop, st);
+        if (r != MVN_E_UNSUPPORTED) return r;               // fewer than 128 rows: the warp-MMA kernel below
+    }
     if (variant == 0) return E == 64 ? launch_fwd_t<64, 1, 16>(a, st) : launch_fwd_t<32, 1, 16>(a, st);
     // measured (scripts/bench_fused.py, C4 token counts): E = 64 is faster with one row tile per warp and 16 warps (73.7 vs 80.9 us),
     // E = 32 with two row tiles per warp (36.9 vs 38.9 us)

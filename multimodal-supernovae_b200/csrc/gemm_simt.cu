@@ -296,6 +296,10 @@ int launch_gemm(const float* A, const float* Bm, float* C, const int32_t* n_rows
             default: MVN_UNSUPPORTED(false, "linear+residual+LayerNorm needs N in {16,32,64,128}, got %d", N);
         }
     }
+    if (M_cap <= 4096) {      // per-sample heads (M = batch): 16-row tiles give 4x the CTAs of the 64-row ones (a K = 1024 head ran on 16 SMs)
+        if (N <= 32) return launch_t<16, 32, false>(a, st);
+        return launch_t<16, 64, false>(a, st);
+    }
     if (N <= 16) return launch_t<64, 16, false>(a, st);
     if (N <= 32) return launch_t<64, 32, false>(a, st);
     return launch_t<64, 64, false>(a, st);

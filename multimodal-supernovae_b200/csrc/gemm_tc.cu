@@ -642,6 +642,8 @@ static float trunc_comp() {
     return v;
 }
 
+float tc_trunc_comp() { return trunc_comp(); }
+
 int launch_gemm_tc(const float* A, const float* Bm, float* C, const int32_t* n_rows_dev, int M_cap, int N, int K, bool b_is_nk,
                    const GemmEpilogue& ep, cudaStream_t st) {
     // shapes this kernel is built for; anything else stays on the FFMA kernel
