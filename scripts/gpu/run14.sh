@@ -1,0 +1,5 @@
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_gpu_tc.py -q -k "attention or seq_encoder" 2>&1 | tail -4 | cut -c1-300
+MVN_ATTN_FWD=1 python scripts/bench_fused.py attn 2>&1 | tail -2
+MVN_ATTN_FWD=2 python scripts/bench_fused.py attn 2>&1 | tail -2
