@@ -22,6 +22,7 @@ constexpr int ATC_THREADS = 128;
 constexpr int CH = 256;                       // keys (or queries) staged in shared memory at a time
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
+constexpr float TRUNC1 = 1.0f + 3.52e-4f;     // mean shrink of one operand the tensor core truncates to TF32 (see gemm_tc.cu::trunc_comp)
 
 // Round-to-nearest TF32 without touching the XU pipe (cvt.rna.tf32 issues there, next to the exp2 the softmax needs):
 // the MMA ignores the low 13 mantissa bits of its operands, so adding half an ulp of TF32 to the bit pattern and letting
@@ -172,18 +173,23 @@ __device__ __forceinline__ void fwd_block(const float* __restrict__ Ks, const fl
     l_lo *= c_lo; l_hi *= c_hi;
 #pragma unroll
     for (int i = 0; i < KS; ++i) { o[i][0] *= c_lo; o[i][1] *= c_lo; o[i][2] *= c_hi; o[i][3] *= c_hi; }
+    // The softmax denominator rides on the tensor core: column HD of the V tile holds 1 for live keys (0 on padding), so one more
+    // MMA per key tile accumulates l = sum_j p_j in an accumulator whose columns all carry the row sum (4 FADDs and the final quad
+    // reduction less).  P goes in as raw fp32 bits: numerator and denominator see the SAME truncated probabilities, so the
+    // truncation cancels in o / l and no rounding add is needed.
+    float la[4] = {l_lo, l_lo, l_hi, l_hi};
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
-        const float p0 = ex2(s[j][0] - mn_lo), p1 = ex2(s[j][1] - mn_lo);
-        const float p2 = ex2(s[j][2] - mn_hi), p3 = ex2(s[j][3] - mn_hi);
-        l_lo += p0 + p1; l_hi += p2 + p3;
-        const float pa[4] = {tf32r(p0), tf32r(p2), tf32r(p1), tf32r(p3)};      // k=t <-> key 2t, k=t+4 <-> key 2t+1
+        const float pa[4] = {ex2(s[j][0] - mn_lo), ex2(s[j][2] - mn_hi), ex2(s[j][1] - mn_lo), ex2(s[j][3] - mn_hi)};      // k=t <-> key 2t, k=t+4 <-> key 2t+1
+        const float* vr = Vs + (kb + j * 8 + 2 * t) * LD;
         float v0[KS], v1[KS];
-        lds_half<HD>(v0, Vs + (kb + j * 8 + 2 * t) * LD + g * KS);
-        lds_half<HD>(v1, Vs + (kb + j * 8 + 2 * t + 1) * LD + g * KS);
+        lds_half<HD>(v0, vr + g * KS);
+        lds_half<HD>(v1, vr + LD + g * KS);
 #pragma unroll
         for (int nt = 0; nt < KS; ++nt) mma_tf32(o[nt], pa, v0[nt], v1[nt]);
+        mma_tf32(la, pa, vr[HD], vr[LD + HD]);
     }
+    l_lo = la[0]; l_hi = la[2];
 }
 
 template <int HD>
@@ -218,6 +224,7 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_fwd_mma_kernel(const float* 
                 __syncthreads();
                 load_slice32<HD, HD>(Ks, base, ld, E + h * HD, k0c, kn, 1.0f);
                 load_slice32<HD>(Vs, base, ld, 2 * E + h * HD, k0c, kn, 1.0f);
+                for (int j = threadIdx.x; j < ((kn + 31) & ~31); j += ATC_THREADS) Vs[j * LD + HD] = j < kn ? 1.0f : 0.0f;      // the ones column (fwd_block)
                 __syncthreads();
             }
             if (!active) continue;
@@ -227,8 +234,7 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_fwd_mma_kernel(const float* 
             if (kb < kpad) fwd_block<HD, 4>(Ks, Vs, kb, kn, qa, o, m_lo, m_hi, l_lo, l_hi, g, t);
         }
         if (!active) continue;
-        l_lo = quad_sum(l_lo); l_hi = quad_sum(l_hi);
-        const float i_lo = 1.0f / l_lo, i_hi = 1.0f / l_hi;
+        const float i_lo = 1.0f / l_lo, i_hi = 1.0f / l_hi;          // l comes out of the ones-column MMA already summed over the row
         const int q_lo = q0 + g, q_hi = q0 + g + 8;
         // accumulator columns under sigma: lane t holds dims [2t*KS, 2t*KS + 2*KS) of rows g (c0,c1) and g+8 (c2,c3)
         float* o_lo = out + (size_t)(r0 + q_lo) * E + h * HD + 2 * t * KS;
@@ -241,8 +247,8 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_fwd_mma_kernel(const float* 
             if (q_hi < n) *reinterpret_cast<float2*>(o_hi) = make_float2(o[0][2] * i_hi, o[0][3] * i_hi);
         }
         if (t == 0) {
-            if (q_lo < n) lse[(size_t)(r0 + q_lo) * H + h] = (m_lo + log2f(l_lo)) * LN2;
-            if (q_hi < n) lse[(size_t)(r0 + q_hi) * H + h] = (m_hi + log2f(l_hi)) * LN2;
+            if (q_lo < n) lse[(size_t)(r0 + q_lo) * H + h] = (m_lo + log2f(l_lo * TRUNC1)) * LN2;      // l was summed from truncated p: undo the mean shrink
+            if (q_hi < n) lse[(size_t)(r0 + q_hi) * H + h] = (m_hi + log2f(l_hi * TRUNC1)) * LN2;
         }
     }
 }
@@ -384,8 +390,8 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
     constexpr int LD = HD + 4;
     __shared__ __align__(16) float As[CH * LD];     // phase 1: K        phase 2: Q
     __shared__ __align__(16) float Bs[CH * LD];     // phase 1: V        phase 2: dO
-    __shared__ float lse_s[CH];                     // phase 2: lse_i * log2e (+inf on padding rows)
-    __shared__ float D_s[CH];                       // phase 2: D_i = dO_i . O_i
+    __shared__ __align__(8) float lse_s[CH];        // phase 2: lse_i * log2e (+inf on padding rows)
+    __shared__ __align__(8) float D_s[CH];                       // phase 2: D_i = dO_i . O_i
     const int b = blockIdx.x / H, h = blockIdx.x % H;
     const int r0 = cu[b], n = cu[b + 1] - r0;
     if (n <= 0) return;
@@ -432,7 +438,10 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
             const int ntile = (kn + 7) >> 3;
             for (int j = 0; j < ntile; ++j) {
                 const int key0 = j * 8;
-                float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+                // The log-sum-exp and D of the tile's two rows are known up front, so they ride in the accumulators' initial values:
+                // the MMAs deliver s - L and dP - D directly (8 FADDs per tile less).  dS feeds the next MMA as raw fp32 bits (the
+                // tensor core truncates them to TF32); the mean shrink of that truncation is folded into the store scale below.
+                float s[4] = {-L_lo, -L_lo, -L_hi, -L_hi}, dp[4] = {-D_lo, -D_lo, -D_hi, -D_hi};
                 float kf[HD / 4], vf[HD / 4];
                 lds_vec<HD>(kf, As + (key0 + g) * LD + t * (HD / 4));
                 lds_vec<HD>(vf, Bs + (key0 + g) * LD + t * (HD / 4));
@@ -443,9 +452,7 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
                 }
                 // no key mask needed: rows of K past the sequence end are zero-filled in shared memory, so whatever (finite) dS
                 // they get multiplies a zero row in the dQ MMA below
-                const float p0 = ex2(s[0] - L_lo), p1 = ex2(s[1] - L_lo);
-                const float p2 = ex2(s[2] - L_hi), p3 = ex2(s[3] - L_hi);
-                const float da[4] = {tf32r(p0 * (dp[0] - D_lo)), tf32r(p2 * (dp[2] - D_hi)), tf32r(p1 * (dp[1] - D_lo)), tf32r(p3 * (dp[3] - D_hi))};
+                const float da[4] = {ex2(s[0]) * dp[0], ex2(s[2]) * dp[2], ex2(s[1]) * dp[1], ex2(s[3]) * dp[3]};
                 float k0[HD / 8], k1[HD / 8];                      // output columns relabelled by sigma
                 lds_half<HD>(k0, As + (key0 + 2 * t) * LD + g * (HD / 8));
                 lds_half<HD>(k1, As + (key0 + 2 * t + 1) * LD + g * (HD / 8));
@@ -454,7 +461,7 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
             }
         }
         if (!active) continue;
-        store_sigma<HD>(dqkv + (size_t)(r0 + q_lo) * ld + h * HD, dqkv + (size_t)(r0 + q_hi) * ld + h * HD, dq, scale, q_lo < n, q_hi < n, t);
+        store_sigma<HD>(dqkv + (size_t)(r0 + q_lo) * ld + h * HD, dqkv + (size_t)(r0 + q_hi) * ld + h * HD, dq, scale * TRUNC1, q_lo < n, q_hi < n, t);
     }
 
     // ---- phase 2: dV_j = sum_i P_ij dO_i ; dK_j = scale * sum_i dS_ij Q_i ; warp owns 16 keys -----------------
@@ -494,7 +501,10 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
             const int ntile = (qn + 7) >> 3;
             for (int j = 0; j < ntile; ++j) {
                 const int qq = j * 8;
-                float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};      // transposed tiles: rows = keys, cols = queries
+                // transposed tiles: rows = keys, cols = queries; -lse and -D of the tile's two query columns are the accumulators' initial values
+                const int qc = qq + 2 * t;
+                const float2 L01 = *reinterpret_cast<const float2*>(lse_s + qc), D01 = *reinterpret_cast<const float2*>(D_s + qc);
+                float s[4] = {-L01.x, -L01.y, -L01.x, -L01.y}, dp[4] = {-D01.x, -D01.y, -D01.x, -D01.y};
                 float qf[HD / 4], gf[HD / 4];
                 lds_vec<HD>(qf, As + (qq + g) * LD + t * (HD / 4));
                 lds_vec<HD>(gf, Bs + (qq + g) * LD + t * (HD / 4));
@@ -503,11 +513,9 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
                     mma_tf32(s, ka[ks], qf[2 * ks], qf[2 * ks + 1]);
                     mma_tf32(dp, va[ks], gf[2 * ks], gf[2 * ks + 1]);
                 }
-                const int qc = qq + 2 * t;
-                const float L0 = lse_s[qc], L1 = lse_s[qc + 1], D0 = D_s[qc], D1 = D_s[qc + 1];
-                const float p0 = ex2(s[0] - L0), p1 = ex2(s[1] - L1), p2 = ex2(s[2] - L0), p3 = ex2(s[3] - L1);   // 0 on padding (L=+inf)
-                const float pa[4] = {tf32r(p0), tf32r(p2), tf32r(p1), tf32r(p3)};
-                const float da[4] = {tf32r(p0 * (dp[0] - D0)), tf32r(p2 * (dp[2] - D0)), tf32r(p1 * (dp[1] - D1)), tf32r(p3 * (dp[3] - D1))};
+                const float p0 = ex2(s[0]), p1 = ex2(s[1]), p2 = ex2(s[2]), p3 = ex2(s[3]);          // 0 on padding (lse = +inf)
+                const float pa[4] = {p0, p2, p1, p3};                                                 // raw fp32 bits: truncated by the MMA,
+                const float da[4] = {p0 * dp[0], p2 * dp[2], p1 * dp[1], p3 * dp[3]};                 // compensated in the store scale
                 float g0[HD / 8], g1[HD / 8], q0v[HD / 8], q1v[HD / 8];
                 lds_half<HD>(g0, Bs + (qq + 2 * t) * LD + g * (HD / 8));
                 lds_half<HD>(g1, Bs + (qq + 2 * t + 1) * LD + g * (HD / 8));
@@ -524,8 +532,8 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
         const int k_lo = k0 + g, k_hi = k0 + g + 8;
         float* row_lo = dqkv + (size_t)(r0 + k_lo) * ld + h * HD;
         float* row_hi = dqkv + (size_t)(r0 + k_hi) * ld + h * HD;
-        store_sigma<HD>(row_lo + E, row_hi + E, dk, scale, k_lo < n, k_hi < n, t);
-        store_sigma<HD>(row_lo + 2 * E, row_hi + 2 * E, dv, 1.0f, k_lo < n, k_hi < n, t);
+        store_sigma<HD>(row_lo + E, row_hi + E, dk, scale * TRUNC1, k_lo < n, k_hi < n, t);
+        store_sigma<HD>(row_lo + 2 * E, row_hi + 2 * E, dv, TRUNC1, k_lo < n, k_hi < n, t);
     }
 }
 
