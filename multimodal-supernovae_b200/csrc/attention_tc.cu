@@ -65,6 +65,27 @@ __device__ __forceinline__ void load_slice(float* dst, const float* __restrict__
         *reinterpret_cast<float4*>(dst + j * LD + d) = make_float4(tf32r(v.x * mul), tf32r(v.y * mul), tf32r(v.z * mul), tf32r(v.w * mul));
     }
 }
+// ---- skewed rows ----------------------------------------------------------------------------------------------------------
+// The backward reads each staged operand in BOTH fragment forms (K-form: row g, HD/4 contiguous floats at t*HD/4, a 64- / 128-bit
+// load; V-form: rows 2t and 2t+1, HD/8 floats at g*HD/8).  No constant row stride is conflict-free for both (HD+4 made one
+// shared-memory wavefront in three of the head-dim-8 backward a bank conflict), a row-dependent skew is:
+//   HD = 8 : row r at 8*(r + r/4)   -> K-form rows r..r+3 on banks {0,8,16,24}+, V-form rows 0,2,4,6 of a tile on {0,16,8,24}+
+//   HD = 16: row r at 16*r + 8*(r/2) -> K-form row pairs on disjoint 16-bank halves, V-form rows 0,2,4,6 on {0,8,16,24}+
+template <int HD>
+__device__ __forceinline__ int rowoff(int r) { return HD == 8 ? 8 * (r + (r >> 2)) : 16 * r + 8 * (r >> 1); }
+template <int HD>
+constexpr int skew_floats(int rows) { return HD == 8 ? 8 * (rows + rows / 4) : 16 * rows + 8 * (rows / 2); }
+// like load_slice (rows up to the next multiple of 8 zero-filled), skewed rows
+template <int HD>
+__device__ __forceinline__ void load_slice_skew(float* dst, const float* __restrict__ src, size_t ld, int col, int row0, int cnt, float mul) {
+    const int pad = (cnt + 7) & ~7;
+    for (int idx = threadIdx.x; idx < pad * (HD / 4); idx += ATC_THREADS) {
+        const int j = idx / (HD / 4), d = (idx % (HD / 4)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < cnt) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)(row0 + j) * ld + col + d));
+        *reinterpret_cast<float4*>(dst + rowoff<HD>(j) + d) = make_float4(tf32r(v.x * mul), tf32r(v.y * mul), tf32r(v.z * mul), tf32r(v.w * mul));
+    }
+}
 // ---- operand relabelling -------------------------------------------------------------------------------------------
 // An MMA's contraction slots and output columns can be assigned to head dimensions in any order as long as both operands
 // (resp. the consumer of the accumulator) agree.  Two assignments make every shared-memory fragment load a vector load:
@@ -387,9 +408,8 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
                                                                    const float* __restrict__ dout, float* __restrict__ dqkv,
                                                                    int E, int H, float scale) {
     pdl_trigger();
-    constexpr int LD = HD + 4;
-    __shared__ __align__(16) float As[CH * LD];     // phase 1: K        phase 2: Q
-    __shared__ __align__(16) float Bs[CH * LD];     // phase 1: V        phase 2: dO
+    __shared__ __align__(16) float As[skew_floats<HD>(CH)];     // phase 1: K        phase 2: Q      (skewed rows: rowoff<HD>)
+    __shared__ __align__(16) float Bs[skew_floats<HD>(CH)];     // phase 1: V        phase 2: dO
     __shared__ __align__(8) float lse_s[CH];        // phase 2: lse_i * log2e (+inf on padding rows)
     __shared__ __align__(8) float D_s[CH];                       // phase 2: D_i = dO_i . O_i
     const int b = blockIdx.x / H, h = blockIdx.x % H;
@@ -430,8 +450,8 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
             const int k0c = c * CH, kn = min(CH, n - k0c);
             if (nchunks > 1 || rd == 0) {
                 __syncthreads();
-                load_slice<HD>(As, base, ld, E + h * HD, k0c, kn, 1.0f);
-                load_slice<HD>(Bs, base, ld, 2 * E + h * HD, k0c, kn, 1.0f);
+                load_slice_skew<HD>(As, base, ld, E + h * HD, k0c, kn, 1.0f);
+                load_slice_skew<HD>(Bs, base, ld, 2 * E + h * HD, k0c, kn, 1.0f);
                 __syncthreads();
             }
             if (!active) continue;
@@ -443,8 +463,8 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
                 // tensor core truncates them to TF32); the mean shrink of that truncation is folded into the store scale below.
                 float s[4] = {-L_lo, -L_lo, -L_hi, -L_hi}, dp[4] = {-D_lo, -D_lo, -D_hi, -D_hi};
                 float kf[HD / 4], vf[HD / 4];
-                lds_vec<HD>(kf, As + (key0 + g) * LD + t * (HD / 4));
-                lds_vec<HD>(vf, Bs + (key0 + g) * LD + t * (HD / 4));
+                lds_vec<HD>(kf, As + rowoff<HD>(key0 + g) + t * (HD / 4));
+                lds_vec<HD>(vf, Bs + rowoff<HD>(key0 + g) + t * (HD / 4));
 #pragma unroll
                 for (int ks = 0; ks < HD / 8; ++ks) {
                     mma_tf32(s, qa[ks], kf[2 * ks], kf[2 * ks + 1]);
@@ -454,8 +474,8 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
                 // they get multiplies a zero row in the dQ MMA below
                 const float da[4] = {ex2(s[0]) * dp[0], ex2(s[2]) * dp[2], ex2(s[1]) * dp[1], ex2(s[3]) * dp[3]};
                 float k0[HD / 8], k1[HD / 8];                      // output columns relabelled by sigma
-                lds_half<HD>(k0, As + (key0 + 2 * t) * LD + g * (HD / 8));
-                lds_half<HD>(k1, As + (key0 + 2 * t + 1) * LD + g * (HD / 8));
+                lds_half<HD>(k0, As + rowoff<HD>(key0 + 2 * t) + g * (HD / 8));
+                lds_half<HD>(k1, As + rowoff<HD>(key0 + 2 * t + 1) + g * (HD / 8));
 #pragma unroll
                 for (int nt = 0; nt < HD / 8; ++nt) mma_tf32(dq[nt], da, k0[nt], k1[nt]);
             }
@@ -479,8 +499,8 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
             const int q0c = c * CH, qn = min(CH, n - q0c);
             if (nchunks > 1 || rd == 0) {
                 __syncthreads();                    // also orders phase-1 readers of As/Bs before the overwrite
-                load_slice<HD>(As, base, ld, h * HD, q0c, qn, 1.0f);
-                load_slice<HD>(Bs, gbase, (size_t)E, 0, q0c, qn, 1.0f);
+                load_slice_skew<HD>(As, base, ld, h * HD, q0c, qn, 1.0f);
+                load_slice_skew<HD>(Bs, gbase, (size_t)E, 0, q0c, qn, 1.0f);
                 const int pad = (qn + 7) & ~7;
                 for (int i = threadIdx.x; i < pad; i += ATC_THREADS) {
                     float Di = 0.f, Li = INFINITY;
@@ -506,8 +526,8 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
                 const float2 L01 = *reinterpret_cast<const float2*>(lse_s + qc), D01 = *reinterpret_cast<const float2*>(D_s + qc);
                 float s[4] = {-L01.x, -L01.y, -L01.x, -L01.y}, dp[4] = {-D01.x, -D01.y, -D01.x, -D01.y};
                 float qf[HD / 4], gf[HD / 4];
-                lds_vec<HD>(qf, As + (qq + g) * LD + t * (HD / 4));
-                lds_vec<HD>(gf, Bs + (qq + g) * LD + t * (HD / 4));
+                lds_vec<HD>(qf, As + rowoff<HD>(qq + g) + t * (HD / 4));
+                lds_vec<HD>(gf, Bs + rowoff<HD>(qq + g) + t * (HD / 4));
 #pragma unroll
                 for (int ks = 0; ks < HD / 8; ++ks) {
                     mma_tf32(s, ka[ks], qf[2 * ks], qf[2 * ks + 1]);
@@ -517,10 +537,10 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
                 const float pa[4] = {p0, p2, p1, p3};                                                 // raw fp32 bits: truncated by the MMA,
                 const float da[4] = {p0 * dp[0], p2 * dp[2], p1 * dp[1], p3 * dp[3]};                 // compensated in the store scale
                 float g0[HD / 8], g1[HD / 8], q0v[HD / 8], q1v[HD / 8];
-                lds_half<HD>(g0, Bs + (qq + 2 * t) * LD + g * (HD / 8));
-                lds_half<HD>(g1, Bs + (qq + 2 * t + 1) * LD + g * (HD / 8));
-                lds_half<HD>(q0v, As + (qq + 2 * t) * LD + g * (HD / 8));
-                lds_half<HD>(q1v, As + (qq + 2 * t + 1) * LD + g * (HD / 8));
+                lds_half<HD>(g0, Bs + rowoff<HD>(qq + 2 * t) + g * (HD / 8));
+                lds_half<HD>(g1, Bs + rowoff<HD>(qq + 2 * t + 1) + g * (HD / 8));
+                lds_half<HD>(q0v, As + rowoff<HD>(qq + 2 * t) + g * (HD / 8));
+                lds_half<HD>(q1v, As + rowoff<HD>(qq + 2 * t + 1) + g * (HD / 8));
 #pragma unroll
                 for (int nt = 0; nt < HD / 8; ++nt) {
                     mma_tf32(dv[nt], pa, g0[nt], g1[nt]);
