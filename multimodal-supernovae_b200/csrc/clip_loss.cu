@@ -269,7 +269,7 @@ extern "C" size_t mvn_clip_loss_workspace_bytes(int n, int N, int D) {
     if (tc_loss_supported(n, N, D)) {                                            // the tensor-core passes split the columns differently
         int rt, ns, tps;
         tc_loss_split(n, N, 128, &rt, &ns, &tps);
-        const size_t f2 = (size_t)4 * ns * n + n;
+        const size_t f2 = (size_t)8 * ns * n + n;                                // two partial (max, sum) slots per column split: one per column half
         tc_loss_split(n, N, 64, &rt, &ns, &tps);
         const size_t b2 = (size_t)2 * ns * n * D + (size_t)ns * rt;
         fwd = fwd > f2 ? fwd : f2;
@@ -299,13 +299,14 @@ extern "C" int mvn_clip_loss_fwd(const float* e1_local, const float* e2_local, c
     if (prec >= 1 && tc_loss_supported(n, N, D)) {
         int rt, ns, tps;
         tc_loss_split(n, N, 128, &rt, &ns, &tps);
-        float* pm_r = ws;                        float* pl_r = pm_r + (size_t)ns * n;
-        float* pm_c = pl_r + (size_t)ns * n;     float* pl_c = pm_c + (size_t)ns * n;
-        float* terms = pl_c + (size_t)ns * n;
+        const size_t np = (size_t)2 * ns * n;                                    // the kernel writes two partial slots per split (column halves)
+        float* pm_r = ws;              float* pl_r = pm_r + np;
+        float* pm_c = pl_r + np;       float* pl_c = pm_c + np;
+        float* terms = pl_c + np;
         MVN_TRY(launch_lse_tc(e2_local, e1_all, n, N, logit_scale, logit_bias, tps, rt, ns, pm_r, pl_r, st));
         MVN_TRY(launch_lse_tc(e1_local, e2_all, n, N, logit_scale, logit_bias, tps, rt, ns, pm_c, pl_c, st));
         count_tier(TIER_TC);
-        lse_finish_kernel<<<cdiv(n * 32, 256), 256, 0, st>>>(pm_r, pl_r, pm_c, pl_c, ns, e1_local, e2_local, n, D, logit_scale, logit_bias,
+        lse_finish_kernel<<<cdiv(n * 32, 256), 256, 0, st>>>(pm_r, pl_r, pm_c, pl_c, 2 * ns, e1_local, e2_local, n, D, logit_scale, logit_bias,
                                                              lse_row, lse_col, terms);
         MVN_LAUNCH_CHECK();
         sum_kernel<<<1, 1024, 0, st>>>(terms, n, 0.5f / (float)N, nullptr, loss_out);

@@ -46,7 +46,8 @@ constexpr int LF_OFF_C = 4 * LT_BOX;              // 65536
 constexpr int LF_OFF_BAR = LF_OFF_C + LF_STAGES * 4 * LT_BOX;      // 196608
 constexpr int LF_OFF_TMEM = LF_OFF_BAR + 16 * 8;
 constexpr int LF_SMEM = LF_OFF_TMEM + 16 + 1024;
-constexpr int LF_THREADS = 192;
+constexpr int LF_EPI = 8;                         // epilogue warps: two per TMEM lane quadrant, each takes half of the tile's columns
+constexpr int LF_THREADS = 32 * (2 + LF_EPI);
 
 struct LseArgs {
     int nr, N, tiles_per_split;
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(LF_THREADS, 1) tc_lse_kernel(const __grid_cons
         tma_prefetch_desc(&tmapC);
         mbar_init(r_full, 1);
         for (int s = 0; s < LF_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), LF_EPI); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(sbase + LF_OFF_TMEM, 256);
@@ -127,8 +128,9 @@ __global__ void __launch_bounds__(LF_THREADS, 1) tc_lse_kernel(const __grid_cons
             if ((buf ^= 1) == 0) tph ^= 1;
         }
     } else {
-        // ===== epilogue: one thread per row, online log-sum-exp in base 2 =====
-        const int quad = warp & 3;
+        // ===== epilogue: one thread per (row, column half), online log-sum-exp in base 2; the two halves of a row are two
+        // partial (max, sum) pairs that lse_finish_kernel merges like column splits =====
+        const int quad = warp & 3, half = (warp - 2) >> 2;
         const int row = m0 + quad * 32 + lane;
         const float s2 = expf(__ldg(a.logit_scale)) * TRUNC2 * LOG2E, b2 = __ldg(a.logit_bias) * LOG2E;
         float m_run = -INFINITY, l_run = 0.f;
@@ -137,10 +139,10 @@ __global__ void __launch_bounds__(LF_THREADS, 1) tc_lse_kernel(const __grid_cons
             const int buf = it & 1;
             mbar_wait(tfull_bar(buf), (it >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + buf * LF_NC + ((uint32_t)(quad * 32) << 16);
-            const int c_base = ct * LF_NC;
+            const uint32_t taddr = tmem_base + buf * LF_NC + half * (LF_NC / 2) + ((uint32_t)(quad * 32) << 16);
+            const int c_base = ct * LF_NC + half * (LF_NC / 2);
 #pragma unroll 1
-            for (int c0 = 0; c0 < LF_NC; c0 += 32) {
+            for (int c0 = 0; c0 < LF_NC / 2; c0 += 32) {
                 float v[32];
                 tmem_ld32(taddr + c0, v);
                 const int lim = a.N - (c_base + c0);                    // columns >= N (zero rows of C from the TMA fill) are excluded
@@ -150,19 +152,22 @@ __global__ void __launch_bounds__(LF_THREADS, 1) tc_lse_kernel(const __grid_cons
                     v[j] = j < lim ? fmaf(v[j], s2, b2) : -INFINITY;
                     tm = fmaxf(tm, v[j]);
                 }
-                if (tm > m_run) { l_run *= ex2f(m_run - tm); m_run = tm; }   // m_run == -inf, tm finite: ex2(-inf) = 0 and l_run is 0 anyway
-                float ps = 0.f;
+                if (tm > m_run) { l_run *= ex2f(m_run - tm); m_run = tm; }
+                if (m_run > -INFINITY) {                                // a column half that lies entirely past N contributes nothing
+                    float ps = 0.f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) ps += ex2f(v[j] - m_run);
-                l_run += ps;
+                    for (int j = 0; j < 32; ++j) ps += ex2f(v[j] - m_run);
+                    l_run += ps;
+                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(buf));
         }
         if (row < a.nr) {
-            a.pm[(size_t)blockIdx.y * a.nr + row] = m_run * LN2;            // natural-log units: lse_finish_kernel merges with expf
-            a.pl[(size_t)blockIdx.y * a.nr + row] = l_run;
+            const size_t slot = ((size_t)blockIdx.y * 2 + half) * a.nr + row;
+            a.pm[slot] = m_run > -INFINITY ? m_run * LN2 : -1e30f;      // natural-log units; an empty half merges as exp(-1e30 - m) * 0 = 0
+            a.pl[slot] = l_run;
         }
     }
     tc_fence_before();
@@ -183,10 +188,11 @@ constexpr int LB_OFF_C = 4 * LT_BOX;                                  // 65536
 constexpr int LB_OFF_G = LB_OFF_C + LB_STAGES * LB_STAGE_BYTES;       // 196608: 2 boxes [128 x 32] = 32 KB
 constexpr int LB_OFF_LSE = LB_OFF_G + 2 * LT_BOX;                     // 229376: lse_C of the tile, double buffered
 constexpr int LB_OFF_RED = LB_OFF_LSE + 2 * LB_NC * 4;
-constexpr int LB_OFF_BAR = LB_OFF_RED + 32;
+constexpr int LB_OFF_BAR = LB_OFF_RED + 64;
 constexpr int LB_OFF_TMEM = LB_OFF_BAR + 16 * 8;
 constexpr int LB_SMEM = LB_OFF_TMEM + 16 + 1024;
-constexpr int LB_THREADS = 192;
+constexpr int LB_EPI = 8;                         // epilogue warps: two per TMEM lane quadrant, each takes 32 of the tile's 64 columns
+constexpr int LB_THREADS = 32 * (2 + LB_EPI);
 static_assert(LB_SMEM <= 232448, "backward tile set exceeds the 227 KB of shared memory per CTA");
 
 struct GradArgs {
@@ -214,9 +220,9 @@ __global__ void __launch_bounds__(LB_THREADS, 1) tc_grad_kernel(const __grid_con
         tma_prefetch_desc(&tmapR);
         tma_prefetch_desc(&tmapCk);
         tma_prefetch_desc(&tmapCm);
-        mbar_init(r_full, 1); mbar_init(g_full, 4); mbar_init(g_empty, 1); mbar_init(d_full, 1);
+        mbar_init(r_full, 1); mbar_init(g_full, LB_EPI); mbar_init(g_empty, 1); mbar_init(d_full, 1);
         for (int s = 0; s < LB_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), LB_EPI); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(sbase + LB_OFF_TMEM, 256);
@@ -297,53 +303,49 @@ __global__ void __launch_bounds__(LB_THREADS, 1) tc_grad_kernel(const __grid_con
             __syncwarp();
         }
     } else {
-        // ===== epilogue: Z -> G (shared memory, K-major), finally dR from TMEM =====
-        const int quad = warp & 3, et = (warp - 2) * 32 + lane;               // et: 0..127 among the epilogue threads
+        // ===== epilogue: Z -> G (shared memory, K-major), finally dR from TMEM; one thread per (row, 32-column half of the tile) =====
+        const int quad = warp & 3, half = (warp - 2) >> 2, et = (warp - 2) * 32 + lane;      // et: 0..255 among the epilogue threads
         const int r = quad * 32 + lane, row = m0 + r;
         const float s_nat = expf(__ldg(a.logit_scale)) * TRUNC2, b_nat = __ldg(a.logit_bias);
         const float s2 = s_nat * LOG2E, b2 = b_nat * LOG2E;
         const float lr2 = row < a.nr ? __ldg(a.lse_R + row) * LOG2E : 0.f;
         const float inv2n = 0.5f / (float)a.N;
         float dls = 0.f;
-        uint8_t* gbox = smem + LB_OFF_G;
+        uint8_t* gbox = smem + LB_OFF_G + half * LT_BOX;
         for (int i = 0; i < ntile; ++i) {
             const int buf = i & 1, c_base = (ct0 + i) * LB_NC;
             if (et < LB_NC) lsec[buf * LB_NC + et] = (c_base + et < a.N) ? __ldg(a.lse_C + c_base + et) * LOG2E : INFINITY;   // +inf: exp -> 0
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(tfull_bar(buf), (uint32_t)(i >> 1) & 1u);
             tc_fence_after();
             mbar_wait(g_empty, (uint32_t)(i & 1) ^ 1u);                        // the second MMA of tile i-1 has read the G boxes
-            const uint32_t taddr = tmem_z + buf * LB_NC + ((uint32_t)(quad * 32) << 16);
-#pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-                float v[32];
-                tmem_ld32(taddr + 32 * h, v);
+            float v[32];
+            tmem_ld32(tmem_z + buf * LB_NC + 32 * half + ((uint32_t)(quad * 32) << 16), v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int c = c_base + 32 * h + j;
-                    const float z2 = fmaf(v[j], s2, b2);
-                    float g = ex2f(z2 - lr2) + ex2f(z2 - lsec[buf * LB_NC + 32 * h + j]);
-                    if (row + a.row_offset == c) g -= 2.0f;
-                    g = (row < a.nr && c < a.N) ? g * inv2n : 0.f;
-                    dls = fmaf(g, z2 - b2, dls);                              // (z - b) in base-2 units; rescaled by ln 2 at the end
-                    v[j] = g;
-                }
-                box_row_write(gbox + h * LT_BOX, r, v);
+            for (int j = 0; j < 32; ++j) {
+                const int c = c_base + 32 * half + j;
+                const float z2 = fmaf(v[j], s2, b2);
+                float g = ex2f(z2 - lr2) + ex2f(z2 - lsec[buf * LB_NC + 32 * half + j]);
+                if (row + a.row_offset == c) g -= 2.0f;
+                g = (row < a.nr && c < a.N) ? g * inv2n : 0.f;
+                dls = fmaf(g, z2 - b2, dls);                                  // (z - b) in base-2 units; rescaled by ln 2 at the end
+                v[j] = g;
             }
+            box_row_write(gbox, r, v);
             tc_fence_before();
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) { mbar_arrive(tempty_bar(buf)); mbar_arrive(g_full); }
         }
-        // dR of this CTA's column range
+        // dR of this CTA's column range: this thread's row, columns 64*half .. +63
         if (ntile > 0) {
             mbar_wait_sleep(d_full, 0);
             tc_fence_after();
         }
-        const uint32_t taddr = tmem_d + ((uint32_t)(quad * 32) << 16);
-        float* o = a.dR_part + ((size_t)blockIdx.y * a.nr + row) * 128;
+        const uint32_t taddr = tmem_d + 64 * half + ((uint32_t)(quad * 32) << 16);
+        float* o = a.dR_part + ((size_t)blockIdx.y * a.nr + row) * 128 + 64 * half;
 #pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
+        for (int c0 = 0; c0 < 64; c0 += 32) {
             float v[32];
             if (ntile > 0) {
                 tmem_ld32(taddr + c0, v);
@@ -360,8 +362,13 @@ __global__ void __launch_bounds__(LB_THREADS, 1) tc_grad_kernel(const __grid_con
         if (a.dls_part) {
             dls = warp_sum(dls * LN2);
             if (lane == 0) red[warp - 2] = dls;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (et == 0) a.dls_part[blockIdx.y * gridDim.x + blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (et == 0) {
+                float t_ = 0.f;
+#pragma unroll
+                for (int w = 0; w < LB_EPI; ++w) t_ += red[w];
+                a.dls_part[blockIdx.y * gridDim.x + blockIdx.x] = t_;
+            }
         }
     }
     tc_fence_before();

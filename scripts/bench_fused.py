@@ -65,6 +65,26 @@ def attn():
               f"  -> per step x{layers}: fwd {tf*layers:.3f} ms bwd {tb*layers:.3f} ms", flush=True)
 
 
+def loss():
+    """one rank's share of the C5 loss at a global batch of 65 536 (n = 8 192 local rows), per pair: forward (2 directions) and backward"""
+    D = 128
+    for (n, N) in [(1024, 1024), (8192, 8192), (8192, 65536)]:
+        torch.manual_seed(0)
+        e1 = torch.nn.functional.normalize(torch.randn(N, D, device=dev), dim=-1); e2 = torch.nn.functional.normalize(torch.randn(N, D, device=dev), dim=-1)
+        ls = torch.tensor([math.log(19.5)], device=dev); lb = torch.tensor([-10.0], device=dev)
+        wsb = L.mvn_clip_loss_workspace_bytes(n, N, D); ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        loss_ = torch.empty(1, device=dev); lse = torch.empty(2, N, device=dev)
+        d1 = torch.empty(n, D, device=dev); d2 = torch.empty(n, D, device=dev); dls = torch.empty(1, device=dev)
+        for prec in (0, 1):
+            fwd = lambda: L.mvn_clip_loss_fwd(P(e1), P(e2), P(e1), P(e2), n, N, D, 0, P(ls), P(lb), P(loss_), P(lse[0]), P(lse[1]), P(ws), wsb, prec, S())
+            bwd = lambda: L.mvn_clip_loss_bwd(P(e1), P(e2), P(e1), P(e2), n, N, D, 0, P(ls), P(lb), P(lse[0]), P(lse[1]), None, P(d1), P(d2), P(dls), P(ws), wsb, prec, S())
+            if prec == 0 and n * N > 1 << 27:
+                continue
+            assert fwd() == 0 and bwd() == 0, L.mvn_last_error()
+            tf, tb = timeit(fwd, 5), timeit(bwd, 5)
+            print(f"clip loss n={n} N={N} prec={prec}: fwd {tf*1e3:.0f} us ({4*n*N*D/tf/1e9:.0f} TFLOP/s)  bwd {tb*1e3:.0f} us ({8*n*N*D/tb/1e9:.0f} TFLOP/s)", flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "ffn"
     globals()[which]()
