@@ -6,7 +6,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmaven_sm100.so")
+LIB_PATH = os.environ.get("MVN_LIB_PATH") or os.path.join(_HERE, "libmaven_sm100.so")      # MVN_LIB_PATH: A/B builds of the same library (scripts/)
 
 MVN_ACT_NONE, MVN_ACT_RELU, MVN_ACT_GELU = 0, 1, 2
 MVN_AGG_MEAN, MVN_AGG_MAX, MVN_AGG_NONE = 0, 1, 2

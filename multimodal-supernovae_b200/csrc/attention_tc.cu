@@ -75,15 +75,30 @@ template <int HD>
 __device__ __forceinline__ int rowoff(int r) { return HD == 8 ? 8 * (r + (r >> 2)) : 16 * r + 8 * (r >> 1); }
 template <int HD>
 constexpr int skew_floats(int rows) { return HD == 8 ? 8 * (rows + rows / 4) : 16 * rows + 8 * (rows / 2); }
-// like load_slice (rows up to the next multiple of 8 zero-filled), skewed rows
+// like load_slice (rows up to the next multiple of 8 zero-filled), skewed rows.  A thread walks one 16-byte column slot down the
+// rows in steps of ATC_THREADS / (HD/4) rows (a multiple of 8, over which rowoff is linear): source and destination advance by
+// constants, no per-element index arithmetic.
 template <int HD>
 __device__ __forceinline__ void load_slice_skew(float* dst, const float* __restrict__ src, size_t ld, int col, int row0, int cnt, float mul) {
+    constexpr int Q = HD / 4, STEP = ATC_THREADS / Q, U = 4;
     const int pad = (cnt + 7) & ~7;
-    for (int idx = threadIdx.x; idx < pad * (HD / 4); idx += ATC_THREADS) {
-        const int j = idx / (HD / 4), d = (idx % (HD / 4)) * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < cnt) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)(row0 + j) * ld + col + d));
-        *reinterpret_cast<float4*>(dst + rowoff<HD>(j) + d) = make_float4(tf32r(v.x * mul), tf32r(v.y * mul), tf32r(v.z * mul), tf32r(v.w * mul));
+    int j = threadIdx.x / Q;
+    const int d = (threadIdx.x % Q) * 4;
+    const float* p = src + (size_t)(row0 + j) * ld + col + d;
+    float* q = dst + rowoff<HD>(j) + d;
+    const size_t pstep = (size_t)STEP * ld;
+    constexpr int QSTEP = skew_floats<HD>(STEP);
+    for (; j < pad; j += U * STEP, p += U * pstep, q += U * QSTEP) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {                               // U loads in flight before the first store
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j + u * STEP < cnt) v[u] = __ldg(reinterpret_cast<const float4*>(p + u * pstep));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (j + u * STEP < pad)
+                *reinterpret_cast<float4*>(q + u * QSTEP) = make_float4(tf32r(v[u].x * mul), tf32r(v[u].y * mul), tf32r(v[u].z * mul), tf32r(v[u].w * mul));
     }
 }
 // ---- operand relabelling -------------------------------------------------------------------------------------------
@@ -107,6 +122,34 @@ __device__ __forceinline__ void lds_half<8>(float* dst, const float* src) { dst[
 template <>
 __device__ __forceinline__ void lds_half<16>(float* dst, const float* src) { const float2 v = *reinterpret_cast<const float2*>(src); dst[0] = v.x; dst[1] = v.y; }
 
+// Lane (g, t)'s share of rows row0+g / row0+g+8 under pi: the HD/4 contiguous floats [t*HD/4, (t+1)*HD/4) of each row, straight from
+// global memory; rows >= limit read as 0.
+template <int HD>
+__device__ __forceinline__ void load_rows_pi(float* lo, float* hi, const float* __restrict__ src, size_t ld, int col, int row0, int limit, int g, int t) {
+    constexpr int W = HD / 4;
+#pragma unroll
+    for (int i = 0; i < W; ++i) lo[i] = hi[i] = 0.f;
+    const int r_lo = row0 + g, r_hi = row0 + g + 8;
+    const float* p = src + (size_t)r_lo * ld + col + t * W;
+    if (r_lo < limit) {
+        if constexpr (W == 4) { const float4 v = __ldg(reinterpret_cast<const float4*>(p)); lo[0] = v.x; lo[1] = v.y; lo[2] = v.z; lo[3] = v.w; }
+        else { const float2 v = __ldg(reinterpret_cast<const float2*>(p)); lo[0] = v.x; lo[1] = v.y; }
+    }
+    if (r_hi < limit) {
+        p += 8 * ld;
+        if constexpr (W == 4) { const float4 v = __ldg(reinterpret_cast<const float4*>(p)); hi[0] = v.x; hi[1] = v.y; hi[2] = v.z; hi[3] = v.w; }
+        else { const float2 v = __ldg(reinterpret_cast<const float2*>(p)); hi[0] = v.x; hi[1] = v.y; }
+    }
+}
+// A-operand fragments under pi from a lane's row shares (load_rows_pi)
+template <int HD>
+__device__ __forceinline__ void afrag_from_rows(float (*a)[4], const float* lo, const float* hi, float mul) {
+#pragma unroll
+    for (int ks = 0; ks < HD / 8; ++ks) {
+        a[ks][0] = tf32r(lo[2 * ks] * mul); a[ks][1] = tf32r(hi[2 * ks] * mul);
+        a[ks][2] = tf32r(lo[2 * ks + 1] * mul); a[ks][3] = tf32r(hi[2 * ks + 1] * mul);
+    }
+}
 // A-operand fragments under pi (16 rows starting at row0) straight from global memory; rows >= limit read as 0.
 template <int HD>
 __device__ __forceinline__ void load_afrag_pi(float (*a)[4], const float* __restrict__ src, size_t ld, int col, int row0, int limit, float mul, int g, int t) {
@@ -125,11 +168,7 @@ __device__ __forceinline__ void load_afrag_pi(float (*a)[4], const float* __rest
         if constexpr (W == 4) { const float4 v = __ldg(reinterpret_cast<const float4*>(p)); hi[0] = v.x; hi[1] = v.y; hi[2] = v.z; hi[3] = v.w; }
         else { const float2 v = __ldg(reinterpret_cast<const float2*>(p)); hi[0] = v.x; hi[1] = v.y; }
     }
-#pragma unroll
-    for (int ks = 0; ks < HD / 8; ++ks) {
-        a[ks][0] = tf32r(lo[2 * ks] * mul); a[ks][1] = tf32r(hi[2 * ks] * mul);
-        a[ks][2] = tf32r(lo[2 * ks + 1] * mul); a[ks][3] = tf32r(hi[2 * ks + 1] * mul);
-    }
+    afrag_from_rows<HD>(a, lo, hi, mul);
 }
 // accumulator tiles whose output columns are under sigma: lane t holds dims [2t*KS, 2t*KS + 2*KS) of rows g (c0,c1) and g+8 (c2,c3)
 template <int HD>
@@ -143,7 +182,8 @@ __device__ __forceinline__ void store_sigma(float* __restrict__ p_lo, float* __r
         if (w_hi) *reinterpret_cast<float2*>(p_hi + 2 * t) = make_float2(acc[0][2] * mul, acc[0][3] * mul);
     }
 }
-// like load_slice, but rows up to the next multiple of 32 are zero-filled (branch-free 32-key blocks)
+// like load_slice, but rows up to the next multiple of 32 are zero-filled (branch-free 32-key blocks).  (The constant-stride walk of
+// load_slice_skew was measured here too: it costs the head-dim-8 forward 8 registers and 12 % -- kept as the index loop.)
 template <int HD, int LD = HD + 4>
 __device__ __forceinline__ void load_slice32(float* dst, const float* __restrict__ src, size_t ld, int col, int row0, int cnt, float mul) {
     const int pad = (cnt + 31) & ~31;
@@ -410,8 +450,8 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
     pdl_trigger();
     __shared__ __align__(16) float As[skew_floats<HD>(CH)];     // phase 1: K        phase 2: Q      (skewed rows: rowoff<HD>)
     __shared__ __align__(16) float Bs[skew_floats<HD>(CH)];     // phase 1: V        phase 2: dO
-    __shared__ __align__(8) float lse_s[CH];        // phase 2: lse_i * log2e (+inf on padding rows)
-    __shared__ __align__(8) float D_s[CH];                       // phase 2: D_i = dO_i . O_i
+    __shared__ __align__(8) float lse_s[CH];        // phase 2: -lse_i * log2e (-inf on padding rows)
+    __shared__ __align__(8) float D_s[CH];                       // phase 2: -D_i = -dO_i . O_i
     const int b = blockIdx.x / H, h = blockIdx.x % H;
     const int r0 = cu[b], n = cu[b + 1] - r0;
     if (n <= 0) return;
@@ -422,6 +462,14 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
     const float* gbase = dout + (size_t)r0 * E + h * HD;
     const int nchunks = (n + CH - 1) / CH;
     const int nrounds = (n + 63) / 64;
+    // lane-constant fragment addresses (tile 0): K-form = row g, HD/4 floats at t*HD/4; V-form = rows 2t / 2t+1, HD/8 floats at g*HD/8
+    constexpr int TS = skew_floats<HD>(8);                          // one 8-row tile further
+    const float* const kform_a = As + rowoff<HD>(g) + t * (HD / 4);
+    const float* const kform_b = Bs + rowoff<HD>(g) + t * (HD / 4);
+    const float* const vform_a0 = As + rowoff<HD>(2 * t) + g * (HD / 8);
+    const float* const vform_a1 = As + rowoff<HD>(2 * t + 1) + g * (HD / 8);
+    const float* const vform_b0 = Bs + rowoff<HD>(2 * t) + g * (HD / 8);
+    const float* const vform_b1 = Bs + rowoff<HD>(2 * t + 1) + g * (HD / 8);
 
     // ---- phase 1: dQ_i = scale * sum_j P_ij (dO_i.V_j - D_i) K_j ; warp owns 16 queries -------------------------
     for (int rd = 0; rd < nrounds; ++rd) {
@@ -430,14 +478,16 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
         const int q_lo = q0 + g, q_hi = q0 + g + 8;
         float qa[HD / 8][4], ga[HD / 8][4];                       // contraction slots relabelled by pi (see the forward)
         load_afrag_pi<HD>(qa, base, ld, h * HD, q0, n, scale * LOG2E, g, t);
-        load_afrag_pi<HD>(ga, gbase, (size_t)E, 0, q0, n, 1.0f, g, t);
-        // D for rows g / g+8: each lane of the quad takes HD/4 of the dims
+        // dO rows once: the A fragments of dP = dO V^T and, against the matching share of O, D = dO . O (each lane of the quad holds
+        // HD/4 of the dims)
         float D_lo = 0.f, D_hi = 0.f, L_lo = INFINITY, L_hi = INFINITY;
+        {
+            float g_lo[HD / 4], g_hi[HD / 4], o_lo[HD / 4], o_hi[HD / 4];
+            load_rows_pi<HD>(g_lo, g_hi, gbase, (size_t)E, 0, q0, n, g, t);
+            load_rows_pi<HD>(o_lo, o_hi, obase, (size_t)E, 0, q0, n, g, t);
+            afrag_from_rows<HD>(ga, g_lo, g_hi, 1.0f);
 #pragma unroll
-        for (int d = 0; d < HD / 4; ++d) {
-            const int dd = t * (HD / 4) + d;
-            if (q_lo < n) D_lo = fmaf(__ldg(gbase + (size_t)q_lo * E + dd), __ldg(obase + (size_t)q_lo * E + dd), D_lo);
-            if (q_hi < n) D_hi = fmaf(__ldg(gbase + (size_t)q_hi * E + dd), __ldg(obase + (size_t)q_hi * E + dd), D_hi);
+            for (int d = 0; d < HD / 4; ++d) { D_lo = fmaf(g_lo[d], o_lo[d], D_lo); D_hi = fmaf(g_hi[d], o_hi[d], D_hi); }
         }
         D_lo = quad_sum(D_lo); D_hi = quad_sum(D_hi);
         if (q_lo < n) L_lo = __ldg(lse + (size_t)(r0 + q_lo) * H + h) * LOG2E;
@@ -456,15 +506,21 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
             }
             if (!active) continue;
             const int ntile = (kn + 7) >> 3;
-            for (int j = 0; j < ntile; ++j) {
-                const int key0 = j * 8;
+            // rowoff is linear over whole 8-row tiles, so every fragment address is (lane constant) + tile * TS: the unrolled loop
+            // addresses shared memory with immediates (the index arithmetic was half of this loop's instructions)
+            const float* pk = kform_a;
+            const float* pv = kform_b;
+            const float* pk0 = vform_a0;
+            const float* pk1 = vform_a1;
+#pragma unroll 4
+            for (int j = 0; j < ntile; ++j, pk += TS, pv += TS, pk0 += TS, pk1 += TS) {
                 // The log-sum-exp and D of the tile's two rows are known up front, so they ride in the accumulators' initial values:
                 // the MMAs deliver s - L and dP - D directly (8 FADDs per tile less).  dS feeds the next MMA as raw fp32 bits (the
                 // tensor core truncates them to TF32); the mean shrink of that truncation is folded into the store scale below.
                 float s[4] = {-L_lo, -L_lo, -L_hi, -L_hi}, dp[4] = {-D_lo, -D_lo, -D_hi, -D_hi};
                 float kf[HD / 4], vf[HD / 4];
-                lds_vec<HD>(kf, As + rowoff<HD>(key0 + g) + t * (HD / 4));
-                lds_vec<HD>(vf, Bs + rowoff<HD>(key0 + g) + t * (HD / 4));
+                lds_vec<HD>(kf, pk);
+                lds_vec<HD>(vf, pv);
 #pragma unroll
                 for (int ks = 0; ks < HD / 8; ++ks) {
                     mma_tf32(s, qa[ks], kf[2 * ks], kf[2 * ks + 1]);
@@ -474,8 +530,8 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
                 // they get multiplies a zero row in the dQ MMA below
                 const float da[4] = {ex2(s[0]) * dp[0], ex2(s[2]) * dp[2], ex2(s[1]) * dp[1], ex2(s[3]) * dp[3]};
                 float k0[HD / 8], k1[HD / 8];                      // output columns relabelled by sigma
-                lds_half<HD>(k0, As + rowoff<HD>(key0 + 2 * t) + g * (HD / 8));
-                lds_half<HD>(k1, As + rowoff<HD>(key0 + 2 * t + 1) + g * (HD / 8));
+                lds_half<HD>(k0, pk0);
+                lds_half<HD>(k1, pk1);
 #pragma unroll
                 for (int nt = 0; nt < HD / 8; ++nt) mma_tf32(dq[nt], da, k0[nt], k1[nt]);
             }
@@ -503,7 +559,7 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
                 load_slice_skew<HD>(Bs, gbase, (size_t)E, 0, q0c, qn, 1.0f);
                 const int pad = (qn + 7) & ~7;
                 for (int i = threadIdx.x; i < pad; i += ATC_THREADS) {
-                    float Di = 0.f, Li = INFINITY;
+                    float Di = 0.f, Li = INFINITY;                      // stored negated: accumulator initial values of the tile loop
                     if (i < qn) {
 #pragma unroll
                         for (int d = 0; d < HD; d += 4) {
@@ -513,34 +569,42 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
                         }
                         Li = __ldg(lse + (size_t)(r0 + q0c + i) * H + h) * LOG2E;
                     }
-                    D_s[i] = Di; lse_s[i] = Li;
+                    D_s[i] = -Di; lse_s[i] = -Li;
                 }
                 __syncthreads();
             }
             if (!active) continue;
             const int ntile = (qn + 7) >> 3;
-            for (int j = 0; j < ntile; ++j) {
-                const int qq = j * 8;
-                // transposed tiles: rows = keys, cols = queries; -lse and -D of the tile's two query columns are the accumulators' initial values
-                const int qc = qq + 2 * t;
-                const float2 L01 = *reinterpret_cast<const float2*>(lse_s + qc), D01 = *reinterpret_cast<const float2*>(D_s + qc);
-                float s[4] = {-L01.x, -L01.y, -L01.x, -L01.y}, dp[4] = {-D01.x, -D01.y, -D01.x, -D01.y};
+            const float* pq = kform_a;
+            const float* pg = kform_b;
+            const float* pq0 = vform_a0;
+            const float* pq1 = vform_a1;
+            const float* pg0 = vform_b0;
+            const float* pg1 = vform_b1;
+            const float* pl = lse_s + 2 * t;
+            const float* pd = D_s + 2 * t;
+#pragma unroll 4
+            for (int j = 0; j < ntile; ++j, pq += TS, pg += TS, pq0 += TS, pq1 += TS, pg0 += TS, pg1 += TS, pl += 8, pd += 8) {
+                // transposed tiles: rows = keys, cols = queries; -lse and -D of the tile's two query columns (stored negated) are the
+                // accumulators' initial values
+                const float2 L01 = *reinterpret_cast<const float2*>(pl), D01 = *reinterpret_cast<const float2*>(pd);
+                float s[4] = {L01.x, L01.y, L01.x, L01.y}, dp[4] = {D01.x, D01.y, D01.x, D01.y};
                 float qf[HD / 4], gf[HD / 4];
-                lds_vec<HD>(qf, As + rowoff<HD>(qq + g) + t * (HD / 4));
-                lds_vec<HD>(gf, Bs + rowoff<HD>(qq + g) + t * (HD / 4));
+                lds_vec<HD>(qf, pq);
+                lds_vec<HD>(gf, pg);
 #pragma unroll
                 for (int ks = 0; ks < HD / 8; ++ks) {
                     mma_tf32(s, ka[ks], qf[2 * ks], qf[2 * ks + 1]);
                     mma_tf32(dp, va[ks], gf[2 * ks], gf[2 * ks + 1]);
                 }
-                const float p0 = ex2(s[0]), p1 = ex2(s[1]), p2 = ex2(s[2]), p3 = ex2(s[3]);          // 0 on padding (lse = +inf)
+                const float p0 = ex2(s[0]), p1 = ex2(s[1]), p2 = ex2(s[2]), p3 = ex2(s[3]);          // 0 on padding (-lse = -inf)
                 const float pa[4] = {p0, p2, p1, p3};                                                 // raw fp32 bits: truncated by the MMA,
                 const float da[4] = {p0 * dp[0], p2 * dp[2], p1 * dp[1], p3 * dp[3]};                 // compensated in the store scale
                 float g0[HD / 8], g1[HD / 8], q0v[HD / 8], q1v[HD / 8];
-                lds_half<HD>(g0, Bs + rowoff<HD>(qq + 2 * t) + g * (HD / 8));
-                lds_half<HD>(g1, Bs + rowoff<HD>(qq + 2 * t + 1) + g * (HD / 8));
-                lds_half<HD>(q0v, As + rowoff<HD>(qq + 2 * t) + g * (HD / 8));
-                lds_half<HD>(q1v, As + rowoff<HD>(qq + 2 * t + 1) + g * (HD / 8));
+                lds_half<HD>(g0, pg0);
+                lds_half<HD>(g1, pg1);
+                lds_half<HD>(q0v, pq0);
+                lds_half<HD>(q1v, pq1);
 #pragma unroll
                 for (int nt = 0; nt < HD / 8; ++nt) {
                     mma_tf32(dv[nt], pa, g0[nt], g1[nt]);
