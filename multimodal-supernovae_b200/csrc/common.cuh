@@ -172,6 +172,7 @@ int launch_wgrad_partials(const float* dY, const float* X, const int32_t* n_rows
                           float* partial, size_t pstride, size_t woff, long long boff, int prec, cudaStream_t st);
 // out[i] = (accumulate? out[i]:0) + sum_s partial[s*pstride + i], i < n
 int launch_reduce_partials(const float* partial, size_t pstride, size_t n, float* out, int accumulate, cudaStream_t st);
+int launch_reduce_partials_n(const float* partial, size_t pstride, size_t n, int nslabs, float* out, int accumulate, cudaStream_t st);
 int launch_ln_bwd(const float* dY, const float* xhat, const float* rstd, const float* gamma, float* dZ,
                   const int32_t* n_rows_dev, int M_cap, int E, float* partial, size_t pstride, size_t goff, size_t boff,
                   cudaStream_t st, const DropCfg& drop = DropCfg());     // drop: dY is the gradient AFTER the dropout that followed this LayerNorm

@@ -584,6 +584,19 @@ inline int ew_blocks(size_t n) { size_t b = (n + 255) / 256; return (int)(b < 40
 bool patch_conv_tc_supported(const mvn_conv_cfg& c);
 int launch_patch_conv_fwd_tc(const mvn_conv_cfg& c, const float* img, const float* Wt, float* u, float* a, double* stat_part, cudaStream_t st);
 int launch_patch_conv_wgrad_tc(const mvn_conv_cfg& c, const float* img, const float* dU, float* partial, size_t pstride, size_t woff, cudaStream_t st);
+// convmixer_fused.cu: one kernel per BatchNorm stage of the mixer layers (dim 32, training mode)
+bool mixer_fused_supported(int dim, int P, int k, int training);
+size_t mixer_scratch_bytes(int B);
+int launch_mixer_fwd(int kind, int k, const double* stats_prev, double count, const float* gamma, const float* beta, float eps, float momentum,
+                     float* running, float* mean_o, float* rstd_o, float* scale_o, float* shift_o, const float* a_prev, const float* res,
+                     float* z_prev, const DropCfg& drop, const float* w, const float* bias, float* u, float* a_out, void* scratch,
+                     double* stats_out, int stage, float* pooled, int B, int Hp, int Wp, cudaStream_t st);
+int launch_mixer_bwd(int kind, int k, float* dZ, const float* a_s, const float* u_s, const float* mean_s, const float* rstd_s, const float* scale_s,
+                     const double* stats_s, double count, const DropCfg& drop_s, const float* w, const float* x, const float* a_p,
+                     const float* mean_p, const float* rstd_p, const DropCfg& drop_p, void* scratch, double* stats_out, float* dgamma,
+                     float* dbeta, int stage, float* dW_out, int B, int Hp, int Wp, cudaStream_t st);
+int launch_pool_bwd_stats(const float* dpooled, float* dZ, const float* a_p, const float* mean_p, const float* rstd_p, const DropCfg& drop_p,
+                          void* scratch, double* stats_out, float* dgamma, float* dbeta, int stage, int B, int P, cudaStream_t st);
 }  // namespace mvn
 
 using namespace mvn;
@@ -652,7 +665,31 @@ extern "C" int mvn_convmixer_fwd_stage(const mvn_conv_cfg* cfg, int stage, const
         MVN_TRY(launch_gemm(w.col, params + o.patch_w, w.bn(0).u, nullptr, R, dim, Kp, true, e, 0, st));
         return gelu_stats(0);
     }
-    MVN_TRY(finish_bn(stage - 1));
+    const bool fused = mixer_fused_supported(dim, P, c.kernel_size, c.training) && mixer_scratch_bytes(c.B) <= (size_t)kSlabs * w.pstride * sizeof(float);      // per-CTA partials live in the weight-gradient slab area
+    if (fused) {
+        // one kernel: BN stage-1 (coefficients, apply, dropout, residual) + this stage's convolution + GELU + the sums of BN `stage`
+        // (or, at the head, + the average pool)
+        const int sp = stage - 1;
+        size_t g, b;
+        bn_param(o, sp, &g, &b);
+        const ConvWs::Bn bp = w.bn(sp);
+        const float* res = (sp & 1) ? w.bn(sp - 1).z : nullptr;
+        const float* cw = nullptr; const float* cb = nullptr;
+        float *uo = nullptr, *ao = nullptr;
+        int kind = 2;
+        if (stage < nbn) {
+            const float* LP = params + o.layer0 + (size_t)((stage - 1) / 2) * o.layer_stride;
+            kind = (stage & 1) ? 0 : 1;
+            cw = LP + (kind == 0 ? o.dw_w : o.pw_w); cb = LP + (kind == 0 ? o.dw_b : o.pw_b);
+            uo = w.bn(stage).u; ao = w.bn(stage).a;
+        }
+        MVN_TRY(launch_mixer_fwd(kind, c.kernel_size, bn_stats + (size_t)sp * 2 * dim, count, params + g, params + b, c.bn_eps, c.bn_momentum,
+                                 running_stats + (size_t)sp * 2 * dim, bp.mean, bp.rstd, bp.scale, bp.shift, bp.a, res, bp.z, conv_drop(c, sp), cw, cb,
+                                 uo, ao, w.partial, bn_stats + (size_t)stage * 2 * dim, stage, w.pooled, c.B, Hp, Wp, st));
+        if (stage < nbn) return 0;
+    } else {
+        MVN_TRY(finish_bn(stage - 1));
+    }
     if (stage < nbn) {
         const int d = (stage - 1) / 2;
         const float* LP = params + o.layer0 + (size_t)d * o.layer_stride;
@@ -669,8 +706,10 @@ extern "C" int mvn_convmixer_fwd_stage(const mvn_conv_cfg* cfg, int stage, const
     }
     // head
     MVN_CHECK_ARG(out != nullptr, "convmixer_fwd_stage: out is null at the last stage");
-    avgpool_fwd_kernel<<<cdiv(c.B * dim, 256), 256, 0, st>>>(w.bn(nbn - 1).z, c.B, P, dim, w.pooled);
-    MVN_LAUNCH_CHECK();
+    if (!fused) {
+        avgpool_fwd_kernel<<<cdiv(c.B * dim, 256), 256, 0, st>>>(w.bn(nbn - 1).z, c.B, P, dim, w.pooled);
+        MVN_LAUNCH_CHECK();
+    }
     GemmEpilogue e1;
     e1.bias = params + o.fc1_b;
     MVN_TRY(launch_gemm(w.pooled, params + o.fc1_w, w.u1, nullptr, c.B, c.hidden, dim, true, e1, 0, st));
@@ -729,6 +768,7 @@ extern "C" int mvn_convmixer_bwd_stage(const mvn_conv_cfg* cfg, int stage, const
         return 0;
     };
 
+    const bool fused = mixer_fused_supported(dim, P, c.kernel_size, c.training) && mixer_scratch_bytes(c.B) <= (size_t)kSlabs * w.pstride * sizeof(float);      // per-CTA partials live in the weight-gradient slab area
     if (stage == nbn) {
         MVN_CHECK_ARG(dout != nullptr, "convmixer_bwd_stage: dout is null at the head stage");
         const int D = c.enc_dim > 0 ? c.enc_dim : c.n_out;
@@ -751,15 +791,35 @@ extern "C" int mvn_convmixer_bwd_stage(const mvn_conv_cfg* cfg, int stage, const
         MVN_TRY(launch_gemm(df, params + o.fc2_w, w.du1, nullptr, c.B, c.hidden, c.n_out, false, eg, 0, st));
         MVN_TRY(launch_wgrad_partials(w.du1, w.pooled, nullptr, c.B, c.hidden, dim, part, ps, o.fc1_w, (long long)o.fc1_b, 0, st));
         MVN_TRY(launch_gemm(w.du1, params + o.fc1_w, w.dpooled, nullptr, c.B, dim, c.hidden, false, e0, 0, st));
+        MVN_TRY(launch_reduce_partials(part + o.fc1_w, ps, o.total - o.fc1_w, grads + o.fc1_w, 0, st));
+        if (fused) {
+            size_t g, b;
+            bn_param(o, nbn - 1, &g, &b);
+            const ConvWs::Bn bl = w.bn(nbn - 1);
+            return launch_pool_bwd_stats(w.dpooled, w.dZ, bl.a, bl.mean, bl.rstd, conv_drop(c, nbn - 1), w.partial,
+                                         bn_stats_bwd + (size_t)(nbn - 1) * 2 * dim, grads + g, grads + b, nbn, c.B, P, st);
+        }
         avgpool_bwd_kernel<<<ew_blocks(n), 256, 0, st>>>(w.dpooled, c.B, P, dim, w.dZ);
         MVN_LAUNCH_CHECK();
-        MVN_TRY(launch_reduce_partials(part + o.fc1_w, ps, o.total - o.fc1_w, grads + o.fc1_w, 0, st));
         return bwd_stats(nbn - 1);
     }
 
     // stage s in [0, nbn): BN s backward (needs the reduced sums), then the convolution that feeds BN s
     const int s = stage;
     const ConvWs::Bn bn = w.bn(s);
+    if (fused && s >= 1) {
+        // one kernel: BN s backward * GELU' -> input gradient of the convolution (+ residual path) = gradient of z_{s-1} (in place in
+        // dZ), the sums of BN s-1 backward (+ dgamma / dbeta), and the convolution's weight-gradient partials
+        const int kind = (s & 1) ? 0 : 1;
+        const size_t lb = o.layer0 + (size_t)((s - 1) / 2) * o.layer_stride;
+        const size_t woff = lb + (kind == 0 ? o.dw_w : o.pw_w);          // the bias follows its weight in the flat layout
+        size_t g, b;
+        bn_param(o, s - 1, &g, &b);
+        const ConvWs::Bn bp = w.bn(s - 1);
+        return launch_mixer_bwd(kind, c.kernel_size, w.dZ, bn.a, bn.u, bn.mean, bn.rstd, bn.scale, bn_stats_bwd + (size_t)s * 2 * dim, count,
+                                conv_drop(c, s), params + woff, bp.z, bp.a, bp.mean, bp.rstd, conv_drop(c, s - 1), w.partial,
+                                bn_stats_bwd + (size_t)(s - 1) * 2 * dim, grads + g, grads + b, s, grads + woff, c.B, Hp, Wp, st);
+    }
     if (c.training) {
         if (dim % 4 == 0 && aligned16(w.dZ) && aligned16(bn.a) && aligned16(bn.u) && aligned16(w.dU))
             bn_bwd_apply_vec_kernel<<<ew_blocks(n / 4), 256, 0, st>>>(w.dZ, bn.a, bn.u, bn.mean, bn.rstd, bn.scale, bn_stats_bwd + (size_t)s * 2 * dim, count,

@@ -40,20 +40,27 @@ __device__ __forceinline__ float4 ld4_guard(const float* __restrict__ p, int row
     return v;
 }
 
-template <int BM, int BN, bool LN>
-__global__ void __launch_bounds__((BM / 4) * (BN / 4)) gemm_kernel(const GemmArgs a) {
+// KS > 1: in-CTA split-K for the per-sample heads (M = batch <= 4096 rows, K up to 1024): KS thread groups of NT threads each
+// own a K range with their own staging tiles, and group 0 adds the partial accumulators in group order (deterministic) before the
+// epilogue.  Without it a K = 1024, N = 32 head is 64 single-warp CTAs walking 64 K-steps each (80 - 190 us per launch).
+template <int BM, int BN, bool LN, int KS = 1>
+__global__ void __launch_bounds__((BM / 4) * (BN / 4) * KS) gemm_kernel(const GemmArgs a) {
     constexpr int NT = (BM / 4) * (BN / 4);
     constexpr int TX = BN / 4;
-    __shared__ __align__(16) float As[BK][BM + 4];
-    __shared__ __align__(16) float Bs[BK][BN + 4];
+    __shared__ __align__(16) float As_[KS][BK][BM + 4];
+    __shared__ __align__(16) float Bs_[KS][BK][BN + 4];
+    __shared__ __align__(16) float red_[KS > 1 ? (KS - 1) * NT * 16 : 4];
 
     const int rows = a.n_rows_dev ? min(*a.n_rows_dev, a.M_cap) : a.M_cap;
     const int m0 = blockIdx.x * BM;
     if (m0 >= rows) return;
     const int n0 = blockIdx.y * BN;
-    const int tid = threadIdx.x;
+    const int ks = threadIdx.x / NT;
+    const int tid = threadIdx.x % NT;
     const int tx = tid % TX, ty = tid / TX;
     const int N = a.N, K = a.K;
+    float (*As)[BM + 4] = As_[ks];
+    float (*Bs)[BN + 4] = Bs_[ks];
 
     float acc[4][4];
 #pragma unroll
@@ -61,7 +68,10 @@ __global__ void __launch_bounds__((BM / 4) * (BN / 4)) gemm_kernel(const GemmArg
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-    for (int k0 = 0; k0 < K; k0 += BK) {
+    const int kper = KS == 1 ? K : ((K + KS * BK - 1) / (KS * BK)) * BK;          // K range of a group, whole BK steps
+    const int kbeg = ks * kper;
+    for (int it = 0; it < kper; it += BK) {                                      // same trip count in every group: the barriers are CTA-wide
+        const int k0 = kbeg + it;
         // A tile: BM rows x BK cols, K contiguous
         for (int idx = tid; idx < BM * (BK / 4); idx += NT) {
             const int r = idx / (BK / 4), kc = (idx % (BK / 4)) * 4;
@@ -94,6 +104,22 @@ __global__ void __launch_bounds__((BM / 4) * (BN / 4)) gemm_kernel(const GemmArg
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
         }
         __syncthreads();
+    }
+    if constexpr (KS > 1) {
+        if (ks > 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<float4*>(&red_[((ks - 1) * NT + tid) * 16 + 4 * i]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        }
+        __syncthreads();
+        if (ks > 0) return;
+#pragma unroll
+        for (int g = 0; g < KS - 1; ++g)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 v = *reinterpret_cast<const float4*>(&red_[(g * NT + tid) * 16 + 4 * i]);
+                acc[i][0] += v.x; acc[i][1] += v.y; acc[i][2] += v.z; acc[i][3] += v.w;
+            }
     }
 
     const GemmEpilogue& ep = a.ep;
@@ -170,10 +196,10 @@ __global__ void __launch_bounds__((BM / 4) * (BN / 4)) gemm_kernel(const GemmArg
     }
 }
 
-template <int BM, int BN, bool LN>
+template <int BM, int BN, bool LN, int KS = 1>
 int launch_t(const GemmArgs& a, cudaStream_t st) {
     dim3 grid(cdiv(a.M_cap, BM), cdiv(a.N, BN));
-    gemm_kernel<BM, BN, LN><<<grid, (BM / 4) * (BN / 4), 0, st>>>(a);
+    gemm_kernel<BM, BN, LN, KS><<<grid, (BM / 4) * (BN / 4) * KS, 0, st>>>(a);
     MVN_LAUNCH_CHECK();
     return 0;
 }
@@ -297,8 +323,8 @@ int launch_gemm(const float* A, const float* Bm, float* C, const int32_t* n_rows
         }
     }
     if (M_cap <= 4096) {      // per-sample heads (M = batch): 16-row tiles give 4x the CTAs of the 64-row ones (a K = 1024 head ran on 16 SMs)
-        if (N <= 32) return launch_t<16, 32, false>(a, st);
-        return launch_t<16, 64, false>(a, st);
+        if (N <= 32) return K >= 256 ? launch_t<16, 32, false, 8>(a, st) : launch_t<16, 32, false>(a, st);
+        return K >= 256 ? launch_t<16, 64, false, 4>(a, st) : launch_t<16, 64, false>(a, st);
     }
     if (N <= 16) return launch_t<64, 16, false>(a, st);
     if (N <= 32) return launch_t<64, 32, false>(a, st);
@@ -321,13 +347,16 @@ int launch_wgrad_partials(const float* dY, const float* X, const int32_t* n_rows
     return 0;
 }
 
-int launch_reduce_partials(const float* partial, size_t pstride, size_t n, float* out, int accumulate, cudaStream_t st) {
+int launch_reduce_partials_n(const float* partial, size_t pstride, size_t n, int nslabs, float* out, int accumulate, cudaStream_t st) {
     if (n == 0) return 0;
     ProfScope prof(PROF_ROW, st);
     const int blocks = (int)((n + 31) / 32);
-    reduce_partials_kernel<<<blocks, 256, 0, st>>>(partial, pstride, n, kSlabs, out, accumulate);
+    reduce_partials_kernel<<<blocks, 256, 0, st>>>(partial, pstride, n, nslabs, out, accumulate);
     MVN_LAUNCH_CHECK();
     return 0;
+}
+int launch_reduce_partials(const float* partial, size_t pstride, size_t n, float* out, int accumulate, cudaStream_t st) {
+    return launch_reduce_partials_n(partial, pstride, n, kSlabs, out, accumulate, st);
 }
 
 }  // namespace mvn

@@ -376,6 +376,28 @@ def test_convmixer_vs_oracle_batch():
     assert relerr(y, ref) < 2 * TOL
 
 
+@pytest.mark.parametrize("dim,depth,k,patch", [(32, 2, 3, 10), (32, 1, 5, 12), (16, 1, 3, 12), (64, 2, 5, 10)])
+def test_convmixer_shapes_vs_oracle(dim, depth, k, patch):
+    """dim 32 runs the one-kernel-per-BatchNorm-stage path (csrc/convmixer_fused.cu: k = 3 and 5, 6x6 and 5x5 maps); other widths run
+    the stage-by-stage kernels of csrc/convmixer.cu.  Forward, every parameter gradient and the running statistics against the
+    float64 oracle."""
+    from maven_b200.models_multimodal import ConvMixer
+    torch.manual_seed(23)
+    B = 37
+    cm = ConvMixer(dim=dim, depth=depth, channels=3, kernel_size=k, patch_size=patch, n_out=32, dropout_prob=0.0)
+    sdg = {kk: (v.detach().double().requires_grad_() if v.is_floating_point() else v.clone()) for kk, v in cm.state_dict().items()}
+    img = torch.rand(B, 3, 60, 60)
+    w = torch.randn(B, 32)
+    cm = cm.to(dev()).train()
+    y = cm(img.to(dev()))
+    (y * w.to(dev())).sum().backward()
+    yr = O.convmixer(sdg, "", img.double(), depth=depth, kernel_size=k, patch_size=patch, training=True)
+    (yr * w.double()).sum().backward()
+    assert relerr(y, yr) < 2 * TOL
+    for kk, p_ in cm.named_parameters():
+        assert relerr(p_.grad, sdg[kk].grad) < GTOL or (p_.grad.cpu() - sdg[kk].grad).abs().max() < 1e-6, kk
+
+
 def test_radam_trajectory_golden(L):
     g = load_golden("radam")
     p = g["params"][0].clone().to(dev())
