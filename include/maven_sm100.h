@@ -154,6 +154,20 @@ int mvn_unpack_rows(const float* X, const int32_t* tok_src, const uint8_t* keyva
 int mvn_pack_rows(const float* dense, const int32_t* tok_src, const uint8_t* keyvalid, const int32_t* n_rows_dev,
                   int BT, int E, float* X, void* stream);
 
+/* agg="attn" in closed form (src/transformer_utils.py:202-207,241-247): nn.MultiheadAttention(emb, H heads, batch_first) with ONE
+ * learnable query over the zero-padded token tensor and NO key mask.  All padded rows are the same key (k = b_k, v = b_v), so a CTA
+ * per sequence reads only the valid rows of x [B,T,E] (mask = uint8 view of the bool [B,T]) and accounts for the T - n padded rows as
+ * one virtual key of that multiplicity; q / k / v / out projections are applied to the query and to the pooled vectors, never to the
+ * B*T tokens.  in_w [3E,E] / in_b [3E] = agg_attn.in_proj_{weight,bias}; out_w / out_b = agg_attn.out_proj.  `saved` (caller-owned,
+ * mvn_attn_pool_saved_bytes) carries q, u, c, lse, xbar, o to the backward, which overwrites dx [B,T,E] and every parameter gradient. */
+size_t mvn_attn_pool_saved_bytes(int B, int E, int H);
+size_t mvn_attn_pool_bwd_workspace_bytes(int B, int E, int H);
+int mvn_attn_pool_fwd(const float* x, const unsigned char* mask, const float* query, const float* in_w, const float* in_b,
+                      const float* out_w, const float* out_b, int B, int T, int E, int H, float* out, float* saved, size_t saved_bytes,
+                      void* stream);
+int mvn_attn_pool_bwd(const float* x, const unsigned char* mask, const float* query, const float* in_w, const float* in_b,
+                      const float* out_w, const float* saved, const float* dout, int B, int T, int E, int H, float* dx, float* dquery,
+                      float* d_in_w, float* d_in_b, float* d_out_w, float* d_out_b, void* workspace, size_t workspace_bytes, void* stream);
 /* A6, agg="attn": nn.MultiheadAttention(E, H) with one learnable query per sequence over the zero-padded tokens, no key
  * mask.  src/transformer_utils.py:241-247.  q[E] = in_proj(query) (shared by all sequences), kv[B*T,2E] = k|v after
  * in_proj (padded rows therefore carry the biases, as in the reference); score scale 1/sqrt(E/H).
@@ -290,6 +304,11 @@ int mvn_weighted_ce_bwd(const float* logits, const int64_t* labels, const float*
                         const float* loss_buf, const float* grad_out, float* dlogits, void* stream);
 int mvn_mse_fwd(const float* pred, const float* target, int n, float* loss, void* stream);
 int mvn_mse_bwd(const float* pred, const float* target, int n, const float* grad_out, float* dpred, void* stream);
+/* masked-light-curve pretraining objective (src/models_pretraining.py:183-226): nn.MSELoss()(x[mask_pred], x_pred[mask_pred]) as a
+ * masked mean over the (B*T) positions; mask = uint8 view of the bool tensor; loss_buf = [loss, number of selected positions]. */
+int mvn_masked_mse_fwd(const float* pred, const float* target, const unsigned char* mask, int n, float* loss_buf, void* stream);
+int mvn_masked_mse_bwd(const float* pred, const float* target, const unsigned char* mask, int n, const float* loss_buf,
+                       const float* grad_out, float* dpred, void* stream);
 
 /* "meta" modality input (src/models_multimodal.py:295-304): out[b] = [ class_emb[cls_b] (half floats) | redshift_b repeated half times ];
  * the backward is the gradient of the embedding table, dclass_emb[c] = sum of dout[b, :half] over rows with cls_b == c (overwritten). */

@@ -55,6 +55,10 @@ _SIGS = {
     "mvn_pool_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P, P]),
     "mvn_unpack_rows": (c_int, [P, P, P, P, c_int, c_int, P, P]),
     "mvn_pack_rows": (c_int, [P, P, P, P, c_int, c_int, P, P]),
+    "mvn_attn_pool_saved_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "mvn_attn_pool_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "mvn_attn_pool_fwd": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, c_size_t, P]),
+    "mvn_attn_pool_bwd": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, c_size_t, P]),
     "mvn_query_pool_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, P]),
     "mvn_query_pool_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, c_size_t, P]),
     "mvn_l2norm_fwd": (c_int, [P, P, P, c_int, c_int, P]),
@@ -81,6 +85,8 @@ _SIGS = {
     "mvn_weighted_ce_bwd": (c_int, [P, P, P, c_int, c_int, P, P, P, P]),
     "mvn_mse_fwd": (c_int, [P, P, c_int, P, P]),
     "mvn_mse_bwd": (c_int, [P, P, c_int, P, P, P]),
+    "mvn_masked_mse_fwd": (c_int, [P, P, P, c_int, P, P]),
+    "mvn_masked_mse_bwd": (c_int, [P, P, P, c_int, P, P, P, P]),
     "mvn_meta_input_fwd": (c_int, [P, P, P, c_int, c_int, c_int, P, P]),
     "mvn_meta_input_bwd": (c_int, [P, P, c_int, c_int, c_int, P, P]),
     "mvn_radam_step": (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, c_float, c_float, P]),

@@ -114,6 +114,36 @@ __global__ void mse_bwd_kernel(const float* __restrict__ a, const float* __restr
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) da[i] = f * (a[i] - b[i]);
 }
 
+// masked-light-curve objective (src/models_pretraining.py:206-226): nn.MSELoss over the positions selected by a bool mask,
+// loss = sum_i m_i (a_i - b_i)^2 / sum_i m_i  (an empty selection gives 0/0 = NaN like the mean of an empty tensor).
+// buf[0] = loss, buf[1] = number of selected positions.
+__global__ void __launch_bounds__(1024) masked_mse_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const unsigned char* __restrict__ m,
+                                                              int n, float* __restrict__ buf) {
+    __shared__ float red[32];
+    __shared__ int redc[32];
+    float s = 0.f;
+    int cnt = 0;
+    for (int i = threadIdx.x; i < n; i += 1024)
+        if (m[i]) { const float d = a[i] - b[i]; s = fmaf(d, d, s); ++cnt; }
+    s = warp_sum(s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = s; redc[threadIdx.x >> 5] = cnt; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = warp_sum(red[threadIdx.x]);
+        cnt = redc[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (threadIdx.x == 0) { buf[0] = s / (float)cnt; buf[1] = (float)cnt; }
+    }
+}
+__global__ void masked_mse_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const unsigned char* __restrict__ m, int n,
+                                      const float* __restrict__ buf, const float* __restrict__ grad_out, float* __restrict__ da) {
+    const float f = 2.0f / buf[1] * (grad_out ? *grad_out : 1.0f);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) da[i] = m[i] ? f * (a[i] - b[i]) : 0.f;
+}
+
 // retrieval rank: one CTA per source j (rows of e2); counts i with cos(e1_i,e2_j) > cos(e1_j,e2_j)
 __global__ void __launch_bounds__(256) ranks_kernel(const float* __restrict__ e1, const float* __restrict__ e2, int N, int D, int32_t* __restrict__ ranks) {
     extern __shared__ float src[];          // e2_j normalised
@@ -197,6 +227,19 @@ extern "C" int mvn_weighted_ce_bwd(const float* logits, const int64_t* labels, c
 extern "C" int mvn_mse_fwd(const float* pred, const float* target, int n, float* loss, void* stream) {
     MVN_CHECK_ARG(pred && target && loss && n > 0, "mse_fwd: bad arguments");
     mse_fwd_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pred, target, n, loss);
+    MVN_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int mvn_masked_mse_fwd(const float* pred, const float* target, const unsigned char* mask, int n, float* loss_buf, void* stream) {
+    MVN_CHECK_ARG(pred && target && mask && loss_buf && n > 0, "masked_mse_fwd: bad arguments");
+    masked_mse_fwd_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pred, target, mask, n, loss_buf);
+    MVN_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int mvn_masked_mse_bwd(const float* pred, const float* target, const unsigned char* mask, int n, const float* loss_buf,
+                                  const float* grad_out, float* dpred, void* stream) {
+    MVN_CHECK_ARG(pred && target && mask && loss_buf && dpred && n > 0, "masked_mse_bwd: bad arguments");
+    masked_mse_bwd_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(pred, target, mask, n, loss_buf, grad_out, dpred);
     MVN_LAUNCH_CHECK();
     return 0;
 }

@@ -290,7 +290,7 @@ class LightCurveImageCLIP(_Base):
         if enc.agg == "pretraining":
             z = tokens
         else:
-            z = ops.linear(enc._attn_pool(tokens), enc.projection.weight, enc.projection.bias, 0)
+            z = ops.linear(enc._attn_pool(tokens, mask), enc.projection.weight, enc.projection.bias, 0)
         z = ops.linear(z, proj.weight, proj.bias, 0)
         return ops.L2NormFn.apply(z) if normalize else z
 

@@ -596,6 +596,46 @@ class QueryPoolFn(torch.autograd.Function):
         return dq.view(qshape), dkv.view(kvshape), None, None, None, None
 
 
+class AttnPoolFn(torch.autograd.Function):
+    """agg='attn' pooling in closed form (mvn_attn_pool_fwd/_bwd): tokens (B,T,E) zero on padding, bool mask (B,T), the learnable
+    query and nn.MultiheadAttention's in_proj / out_proj parameters -> pooled (B,E).  One kernel forward; the k|v projection of the
+    B*T tokens of the per-op path is never formed."""
+
+    @staticmethod
+    def forward(ctx, tokens, mask, query, in_w, in_b, out_w, out_b, H: int):
+        L = lib()
+        tokens = _req(tokens, "tokens")
+        B, T, E = tokens.shape
+        m = _mask_u8(mask, "mask")
+        ps = [_req(t, n) for t, n in ((query, "query"), (in_w, "in_proj_weight"), (in_b, "in_proj_bias"), (out_w, "out_proj.weight"), (out_b, "out_proj.bias"))]
+        out = torch.empty(B, E, dtype=torch.float32, device=tokens.device)
+        saved = torch.empty(L.mvn_attn_pool_saved_bytes(B, E, H) // 4, dtype=torch.float32, device=tokens.device)
+        check(L.mvn_attn_pool_fwd(_p(tokens), _p(m), *[_p(t) for t in ps], B, T, E, H, _p(out), _p(saved), saved.numel() * 4, _stream()), "attn_pool_fwd")
+        _count(1)
+        ctx.save_for_backward(tokens, m, *ps, saved)
+        ctx.dims = (B, T, E, H)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = lib()
+        tokens, m, query, in_w, in_b, out_w, out_b, saved = ctx.saved_tensors
+        B, T, E, H = ctx.dims
+        dout = _req(dout, "grad_output")
+        dx = torch.empty_like(tokens)
+        g = [torch.empty_like(t) for t in (query, in_w, in_b, out_w, out_b)]
+        wsb = L.mvn_attn_pool_bwd_workspace_bytes(B, E, H)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dout.device)
+        check(L.mvn_attn_pool_bwd(_p(tokens), _p(m), _p(query), _p(in_w), _p(in_b), _p(out_w), _p(saved), _p(dout), B, T, E, H, _p(dx),
+                                  *[_p(t) for t in g], _p(ws), wsb, _stream()), "attn_pool_bwd")
+        _count(5 + H)
+        return (dx, None, *g, None)
+
+
+def attn_pool_supported(T: int, E: int, H: int) -> bool:
+    return E <= 128 and 128 % E == 0 and H <= 8 and E % H == 0 and H * T * 4 <= 96 * 1024
+
+
 # ------------------------------------------------------------------------------------------------------
 # CLIP loss (A10/A11)
 # ------------------------------------------------------------------------------------------------------
@@ -846,6 +886,37 @@ class MSEFn(torch.autograd.Function):
         check(L.mvn_mse_bwd(_p(pred), _p(target), pred.numel(), _p(g), _p(d), _stream()), "mse_bwd")
         _count(1)
         return d, None
+
+
+class MaskedMSEFn(torch.autograd.Function):
+    """nn.MSELoss()(target[mask], pred[mask]) without the gather (src/models_pretraining.py:204-205, 221-222): mean of the squared
+    differences over the positions where `mask` is set.  Returns (loss, number of selected positions)."""
+
+    @staticmethod
+    def forward(ctx, pred, target, mask):
+        L = lib()
+        ctx.pred_shape = pred.shape
+        pred = _req(pred, "pred").reshape(-1); target = _req(target, "target").reshape(-1)
+        m = _mask_u8(mask.reshape(-1), "mask_pred")
+        if not (pred.numel() == target.numel() == m.numel()):
+            raise ValueError("masked_mse: size mismatch")
+        buf = torch.empty(2, dtype=torch.float32, device=pred.device)
+        check(L.mvn_masked_mse_fwd(_p(pred), _p(target), _p(m), pred.numel(), _p(buf), _stream()), "masked_mse_fwd")
+        _count(1)
+        ctx.save_for_backward(pred, target, m, buf)
+        loss, cnt = buf[0], buf[1]
+        ctx.mark_non_differentiable(cnt)
+        return loss, cnt
+
+    @staticmethod
+    def backward(ctx, g, _gcount):
+        L = lib()
+        pred, target, m, buf = ctx.saved_tensors
+        d = torch.empty_like(pred)
+        g = _req(g.reshape(1), "grad_output")
+        check(L.mvn_masked_mse_bwd(_p(pred), _p(target), _p(m), pred.numel(), _p(buf), _p(g), _p(d), _stream()), "masked_mse_bwd")
+        _count(1)
+        return d.view(ctx.pred_shape), None, None
 
 
 class _DPWeightedMeanFn(torch.autograd.Function):

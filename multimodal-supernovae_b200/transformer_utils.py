@@ -214,15 +214,20 @@ class TransformerWithTimeEmbeddings(nn.Module):
         tokens = self.run_fused(x, t, mask, group=g, pidx=(0, len(ps)), extra_params=ps, agg_code=_lib.MVN_AGG_NONE, enc_dim=0, normalize=False)
         if self.agg == "pretraining":
             return tokens
-        pooled = self._attn_pool(tokens)
+        pooled = self._attn_pool(tokens, mask)
         return ops.linear(pooled, self.projection.weight, self.projection.bias, 0)
 
-    def _attn_pool(self, tokens):
+    attn_pool_closed_form = True        # False: the per-op path (k|v projection of all B*T tokens), kept for shapes the kernel does not cover and for A/B
+
+    def _attn_pool(self, tokens, mask=None):
         """agg='attn' (:241-247): nn.MultiheadAttention(emb, 2 heads) with a learnable query over the zero-padded
         tokens and NO key mask.  One query per sequence."""
         B, T, E = tokens.shape
+        H = self.agg_attn.num_heads
         w, b = self.agg_attn.in_proj_weight, self.agg_attn.in_proj_bias
+        if self.attn_pool_closed_form and mask is not None and ops.attn_pool_supported(T, E, H):
+            return ops.AttnPoolFn.apply(tokens, mask, self.query, w, b, self.agg_attn.out_proj.weight, self.agg_attn.out_proj.bias, H)
         q = ops.linear(self.query.view(1, E), w[:E], b[:E], 0)                       # (1,E) same for every sequence
         kv = ops.linear(tokens, w[E:], b[E:], 0)                                     # (B,T,2E) = k|v
-        o = ops.QueryPoolFn.apply(q, kv, B, T, E, 2)                                 # (B,E)
+        o = ops.QueryPoolFn.apply(q, kv, B, T, E, H)                                 # (B,E)
         return ops.linear(o, self.agg_attn.out_proj.weight, self.agg_attn.out_proj.bias, 0)

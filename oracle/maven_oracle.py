@@ -153,6 +153,26 @@ def seq_encoder(sd: SD, p: str, x: Tensor, t: Tensor, mask: Tensor, *, emb: int,
 
 
 # --------------------------------------------------------------------------------------
+# N4  masked-light-curve pretraining objective            src/models_pretraining.py:147-226
+# net = TransformerWithTimeEmbeddings(agg="pretraining") -> last_layer Linear(emb, 1) -> squeeze; the loss is
+# nn.MSELoss()(x[mask_pred], x_pred[mask_pred]) with the run selected by mask_in zeroed in the input and the encoder
+# attending over the whole padding mask (:201-203).  The masks are inputs here (the reference draws them on the host).
+# --------------------------------------------------------------------------------------
+def masked_lc_pred(sd: SD, x: Tensor, t: Tensor, padding_mask: Tensor, mask_in: Tensor, *, emb: int, heads: int, depth: int,
+                   nband: int = 1, time_norm: float = 10000.0) -> Tensor:
+    xm = x.clone()
+    xm[~mask_in] = 0
+    h = seq_encoder(sd, "net.", xm[..., None], t, padding_mask, emb=emb, heads=heads, depth=depth, nband=nband,
+                    agg="pretraining", time_norm=time_norm)
+    return F.linear(h, sd["last_layer.weight"], sd["last_layer.bias"]).squeeze(2)
+
+
+def masked_lc_loss(sd: SD, x: Tensor, t: Tensor, padding_mask: Tensor, mask_in: Tensor, mask_pred: Tensor, **kw) -> Tensor:
+    x_pred = masked_lc_pred(sd, x, t, padding_mask, mask_in, **kw)
+    return F.mse_loss(x_pred[mask_pred], x[mask_pred])
+
+
+# --------------------------------------------------------------------------------------
 # A8  ConvMixer.forward                                   src/models_multimodal.py:38-95
 # BatchNorm in train mode uses biased batch variance to normalise and updates running stats
 # with momentum 0.1 / unbiased variance.  `stats_out`, when given, receives the new buffers.

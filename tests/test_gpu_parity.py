@@ -188,6 +188,42 @@ def test_seq_encoder_golden(name):
         assert relerr(got, ref) < GTOL or (got.cpu() - ref).abs().max() < 1e-6, k
 
 
+@pytest.mark.parametrize("emb,heads,T,nband", [(32, 2, 220, 1), (64, 8, 200, 2), (128, 4, 1024, 1)])
+def test_attn_pool_closed_form(emb, heads, T, nband):
+    """agg="attn" (src/transformer_utils.py:202-207,241-247) in closed form (one kernel, the T - n padded rows as one virtual key)
+    against the float64 oracle AND against the per-op path (k|v projection of all B*T tokens): output, token-parameter and
+    pooling-parameter gradients.  Includes a fully valid sequence (no padded rows) and one with a single valid token."""
+    from maven_b200.transformer_utils import TransformerWithTimeEmbeddings
+    gen = torch.Generator().manual_seed(31)
+    B = 9
+    x, t, m = ragged(gen, B, T, nband, 300.0, 1, T // nband)
+    m[0] = True; t[0] = torch.sort(torch.rand(T, generator=gen) * 300.0)[0]; x[0] = torch.randn(T, generator=gen)       # no padding at all
+    m[1] = False; m[1, 0] = True; x[1, 1:] = 0; t[1, 1:] = 0                                                             # one valid token
+    kw = dict(n_out=16, nband=nband, agg="attn", time_norm=20583.37, emb=emb, heads=heads, depth=1)
+    torch.manual_seed(8)
+    enc = TransformerWithTimeEmbeddings(dropout=0.0, **kw)
+    sd = {k: v.detach().double().requires_grad_() for k, v in enc.state_dict().items()}
+    w = torch.randn(B, 16, generator=gen)
+    okw = {k: kw[k] for k in ("emb", "heads", "depth", "nband", "agg", "time_norm")}
+    yr = O.seq_encoder(sd, "", x.double()[..., None], t.double(), m, **okw)
+    (yr * w.double()).sum().backward()
+    enc = enc.to(dev())
+    outs = {}
+    for closed in (True, False):
+        enc.attn_pool_closed_form = closed
+        enc.zero_grad(set_to_none=True)
+        y = enc(x[..., None].to(dev()), t.to(dev()), m.to(dev()))
+        (y * w.to(dev())).sum().backward()
+        outs[closed] = (y.detach().clone(), {k: p.grad.detach().clone() for k, p in enc.named_parameters()})
+    y, grads = outs[True]
+    assert relerr(y, outs[False][0]) < TOL
+    assert relerr(y, yr) < 5e-4          # the fp32 time embedding of ~300-day arguments vs float64 (App. B-1), not the pooling
+    for k, gr in grads.items():
+        assert relerr(gr, outs[False][1][k]) < GTOL or (gr - outs[False][1][k]).abs().max() < 1e-6, k
+        if k.startswith(("agg_attn", "query", "projection")):
+            assert relerr(gr, sd[k].grad) < 2e-3 or (gr.cpu() - sd[k].grad).abs().max() < 1e-6, k
+
+
 @pytest.mark.parametrize("case", ["lc", "sp"])
 def test_seq_encoder_vs_oracle_full_shapes(case):
     """BASELINE shapes (T=200 two-band E64 h8 / T=220 E32 h2) at a batch the oracle finishes in seconds."""

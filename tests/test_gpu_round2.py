@@ -152,3 +152,37 @@ def test_default_constructed_model_fails_fast():
     x = torch.zeros(2, 8, device=dev()); t = torch.zeros(2, 8, device=dev()); mk = torch.ones(2, 8, dtype=torch.bool, device=dev())
     with pytest.raises(RuntimeError, match="emb=256 not in"):                 # the supported grid is stated in INTEGRATION.md
         m(None, x, t, mk, x, t, mk)
+
+
+def test_masked_lc_pretraining_golden():
+    """N4: MaskedLightCurveEncoder (src/models_pretraining.py:106-226) -- fused encoder with agg="pretraining", last_layer GEMM and the
+    masked-MSE kernel against the unmodified reference's training_step: same run selection (random.seed), prediction, loss,
+    every parameter gradient."""
+    import ast
+    import random
+
+    from maven_b200.models_pretraining import MaskedLightCurveEncoder
+    g = load_golden("pretrain_lc")
+    cfg = ast.literal_eval(g["cfg"])
+    sd, grads, _ = split_golden(g)
+    m = MaskedLightCurveEncoder(f_mask=0.25, nband=2, transformer_kwargs=dict(cfg), optimizer_kwargs={}, lr_scheduler_kwargs={}, lr=1e-3)
+    m.load_state_dict(sd)
+    m = m.to(dev()).train()
+    x, t, mask = g["x"].to(dev()), g["t"].to(dev()), g["mask"].to(dev())
+    random.seed(int(g["random_seed"]))
+    x_pred, mask_pred = m.masked_forward(x, t, mask, f_mask=0.25)
+    assert torch.equal(mask_pred.cpu(), g["mask_pred"])
+    assert relerr(x_pred, g["x_pred"]) < TOL
+    random.seed(int(g["random_seed"]))
+    loss = m.training_step((t, x, mask), 0)
+    assert abs(float(loss.detach()) - float(g["loss"])) < TOL * abs(float(g["loss"]))
+    loss.backward()
+    for k, p in m.named_parameters():
+        got = p.grad if p.grad is not None else torch.zeros_like(p)          # agg="pretraining" never touches net.projection
+        assert relerr(got, grads[k]) < GTOL or (got.cpu() - grads[k]).abs().max() < 1e-6, k
+    # the 9-tuple batch of the simulation loader takes the same path (src/models_pretraining.py:223-226)
+    random.seed(int(g["random_seed"]))
+    loss9 = m.validation_step((None, x, t, mask, None, None, None, None, None), 0)
+    assert torch.equal(loss9, loss)
+    xs, ps = m.masked_pred(x, t, mask, f_mask=0.25)
+    assert xs.shape == ps.shape and xs.ndim == 1

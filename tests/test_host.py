@@ -187,3 +187,21 @@ def test_dp_weighted_mean_is_identity_without_group():
     from maven_b200 import ops
     x = torch.tensor(3.0, requires_grad=True)
     assert ops.dp_weighted_mean(x, 5.0) is x
+
+
+def test_pretraining_masks_match_reference_golden():
+    """get_random_mask / get_continous_random_mask (src/models_pretraining.py:17-103) consume torch's / Python's random streams in
+    the reference's order: with the fixture's seeds they select exactly the positions the unmodified reference selected."""
+    import random
+
+    from conftest import load_golden
+    from maven_b200.models_pretraining import get_continous_random_mask, get_random_mask
+    g = load_golden("pretrain_masks")
+    torch.manual_seed(int(g["torch_seed"]))
+    m_in, m_pred = get_random_mask(g["mask"], f_mask=float(g["f_rand"]))
+    assert torch.equal(m_in, g["rand_in"]) and torch.equal(m_pred, g["rand_pred"])
+    random.seed(int(g["random_seed"]))
+    m_in, m_pred = get_continous_random_mask(g["mask"], int(g["nband"]), f_mask=float(g["f_cont"]))
+    assert torch.equal(m_in, g["cont_in"]) and torch.equal(m_pred, g["cont_pred"])
+    # every selected position is valid, the two masks partition the padding mask
+    assert torch.equal(m_in | m_pred, g["mask"]) and not (m_in & m_pred).any()

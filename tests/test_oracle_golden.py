@@ -206,3 +206,21 @@ def test_noisy_loader_golden():
         assert torch.equal(O.noisy_seq(g["mag"], g["magerr"], g[f"{case}.noise_mag"], lvl), g[f"{case}.out1"]), case
     for case in ("lc_sp", "all"):
         assert torch.equal(O.noisy_seq(g["spec"], g["specerr"], g[f"{case}.noise_spec"], lvl), g[f"{case}.out4"]), case
+
+
+def test_masked_lc_pretraining_objective():
+    """N4: MaskedLightCurveEncoder.training_step of the unmodified reference (src/models_pretraining.py:106-226) with the run
+    selection it drew: prediction, loss and every parameter gradient."""
+    g = load_golden("pretrain_lc")
+    cfg = ast.literal_eval(g["cfg"])
+    sd, grads, _ = split_golden(g)
+    sd = _leafify(sd)
+    kw = dict(emb=cfg["emb"], heads=cfg["heads"], depth=cfg["depth"], nband=2, time_norm=cfg["time_norm"])
+    x_pred = O.masked_lc_pred(sd, g["x"], g["t"], g["mask"], g["mask_in"], **kw)
+    assert relerr(x_pred, g["x_pred"]) < TOL
+    loss = O.masked_lc_loss(sd, g["x"], g["t"], g["mask"], g["mask_in"], g["mask_pred"], **kw)
+    assert abs(float(loss.detach()) - float(g["loss"])) < 2e-6 * abs(float(g["loss"]))
+    loss.backward()
+    for k, ref in grads.items():
+        got = sd[k].grad if sd[k].grad is not None else torch.zeros_like(ref)
+        assert relerr(got, ref) < 5e-5 or (got - ref).abs().max() < 1e-6, k
