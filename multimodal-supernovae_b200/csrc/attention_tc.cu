@@ -65,6 +65,13 @@ __device__ __forceinline__ void load_slice(float* dst, const float* __restrict__
         *reinterpret_cast<float4*>(dst + j * LD + d) = make_float4(tf32r(v.x * mul), tf32r(v.y * mul), tf32r(v.z * mul), tf32r(v.w * mul));
     }
 }
+// cp.async: 16 bytes global -> shared without passing through registers; src_bytes = 0 zero-fills
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, int src_bytes) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 // ---- skewed rows ----------------------------------------------------------------------------------------------------------
 // The backward reads each staged operand in BOTH fragment forms (K-form: row g, HD/4 contiguous floats at t*HD/4, a 64- / 128-bit
 // load; V-form: rows 2t and 2t+1, HD/8 floats at g*HD/8).  No constant row stride is conflict-free for both (HD+4 made one
@@ -99,6 +106,17 @@ __device__ __forceinline__ void load_slice_skew(float* dst, const float* __restr
         for (int u = 0; u < U; ++u)
             if (j + u * STEP < pad)
                 *reinterpret_cast<float4*>(q + u * QSTEP) = make_float4(tf32r(v[u].x * mul), tf32r(v[u].y * mul), tf32r(v[u].z * mul), tf32r(v[u].w * mul));
+    }
+}
+// asynchronous version (cp.async, raw fp32 bits: the tensor core truncates them, callers fold TRUNC1 into the other operand / the
+// output scale); rows up to the next multiple of 8 zero-filled
+template <int HD>
+__device__ __forceinline__ void load_slice_skew_async(float* dst, const float* __restrict__ src, size_t ld, int col, int row0, int cnt) {
+    const int pad = (cnt + 7) & ~7;
+    for (int idx = threadIdx.x; idx < pad * (HD / 4); idx += ATC_THREADS) {
+        const int j = idx / (HD / 4), d = (idx % (HD / 4)) * 4;
+        const int jr = j < cnt ? j : cnt - 1;
+        cp_async16(dst + rowoff<HD>(j) + d, src + (size_t)(row0 + jr) * ld + col + d, j < cnt ? 16 : 0);
     }
 }
 // ---- operand relabelling -------------------------------------------------------------------------------------------
@@ -195,6 +213,23 @@ __device__ __forceinline__ void load_slice32(float* dst, const float* __restrict
     }
 }
 
+// ---- asynchronous staging --------------------------------------------------------------------------------------------------
+// Half of the forward's warp-time was spent before its first MMA (ncu source sampling: 45 % of the samples in the prologue, stalled on
+// three dependent global round trips: cu -> Q rows -> K / V rows -> st.shared -> barrier).  K and V now go global -> shared with
+// cp.async (no registers, no conversion) and are in flight together with the Q loads.  The raw fp32 bits are truncated to TF32 by the
+// tensor core instead of being rounded here; the mean shrink of that truncation (TRUNC1) is folded into the Q scale (K) and the
+// output scale (V), which leaves the same zero-mean error as rounding to nearest.
+// rows [row0, row0+cnt) of a column slice -> smem [pad32(cnt)][LD], rows past cnt zero-filled (src-size 0)
+template <int HD, int LD>
+__device__ __forceinline__ void load_slice32_async(float* dst, const float* __restrict__ src, size_t ld, int col, int row0, int cnt) {
+    const int pad = (cnt + 31) & ~31;
+    for (int idx = threadIdx.x; idx < pad * (HD / 4); idx += ATC_THREADS) {
+        const int j = idx / (HD / 4), d = (idx % (HD / 4)) * 4;
+        const int jr = j < cnt ? j : cnt - 1;                          // keep the (unread) address in bounds
+        cp_async16(dst + j * LD + d, src + (size_t)(row0 + jr) * ld + col + d, j < cnt ? 16 : 0);
+    }
+}
+
 // One block of NT key tiles (8 keys each) of the streaming softmax, no per-tile guards: K/V rows past the sequence end are
 // zero in shared memory and only the block that straddles the end (`tail`) masks its scores.
 template <int HD, int NT>
@@ -272,8 +307,16 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_fwd_mma_kernel(const float* 
     for (int rd = 0; rd < nrounds; ++rd) {
         const int q0 = rd * 64 + warp * 16;
         const bool active = q0 < n;
+        float q_lo_[HD / 4], q_hi_[HD / 4];
+        load_rows_pi<HD>(q_lo_, q_hi_, base, ld, h * HD, q0, n, g, t);      // issued first: their latency runs under the cp.async issue below
+        if (nchunks == 1 && rd == 0) {                  // the usual case (n <= CH): K / V in flight while the Q rows are fetched
+            load_slice32_async<HD, HD>(Ks, base, ld, E + h * HD, 0, n);
+            load_slice32_async<HD, LD>(Vs, base, ld, 2 * E + h * HD, 0, n);
+            cp_async_commit();
+            for (int j = threadIdx.x; j < ((n + 31) & ~31); j += ATC_THREADS) Vs[j * LD + HD] = j < n ? 1.0f : 0.0f;      // the ones column (fwd_block)
+        }
         float qa[KS][4];
-        load_afrag_pi<HD>(qa, base, ld, h * HD, q0, n, scale * LOG2E, g, t);      // scores come out in log2 units
+        afrag_from_rows<HD>(qa, q_lo_, q_hi_, scale * LOG2E * TRUNC1);      // scores come out in log2 units; TRUNC1: K is truncated by the MMA
         float o[KS][4];
 #pragma unroll
         for (int i = 0; i < KS; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
@@ -281,11 +324,16 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_fwd_mma_kernel(const float* 
 
         for (int c = 0; c < nchunks; ++c) {
             const int k0c = c * CH, kn = min(CH, n - k0c);
-            if (nchunks > 1 || rd == 0) {
+            if (nchunks > 1) {
                 __syncthreads();
-                load_slice32<HD, HD>(Ks, base, ld, E + h * HD, k0c, kn, 1.0f);
-                load_slice32<HD>(Vs, base, ld, 2 * E + h * HD, k0c, kn, 1.0f);
-                for (int j = threadIdx.x; j < ((kn + 31) & ~31); j += ATC_THREADS) Vs[j * LD + HD] = j < kn ? 1.0f : 0.0f;      // the ones column (fwd_block)
+                load_slice32_async<HD, HD>(Ks, base, ld, E + h * HD, k0c, kn);
+                load_slice32_async<HD, LD>(Vs, base, ld, 2 * E + h * HD, k0c, kn);
+                cp_async_commit();
+                for (int j = threadIdx.x; j < ((kn + 31) & ~31); j += ATC_THREADS) Vs[j * LD + HD] = j < kn ? 1.0f : 0.0f;
+                cp_async_wait_all();
+                __syncthreads();
+            } else if (rd == 0) {
+                cp_async_wait_all();
                 __syncthreads();
             }
             if (!active) continue;
@@ -295,7 +343,7 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_fwd_mma_kernel(const float* 
             if (kb < kpad) fwd_block<HD, 4>(Ks, Vs, kb, kn, qa, o, m_lo, m_hi, l_lo, l_hi, g, t);
         }
         if (!active) continue;
-        const float i_lo = 1.0f / l_lo, i_hi = 1.0f / l_hi;          // l comes out of the ones-column MMA already summed over the row
+        const float i_lo = TRUNC1 / l_lo, i_hi = TRUNC1 / l_hi;      // l comes out of the ones-column MMA already summed over the row; TRUNC1: V is truncated by the MMA
         const int q_lo = q0 + g, q_hi = q0 + g + 8;
         // accumulator columns under sigma: lane t holds dims [2t*KS, 2t*KS + 2*KS) of rows g (c0,c1) and g+8 (c2,c3)
         float* o_lo = out + (size_t)(r0 + q_lo) * E + h * HD + 2 * t * KS;
@@ -476,8 +524,13 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
         const int q0 = rd * 64 + warp * 16;
         const bool active = q0 < n;
         const int q_lo = q0 + g, q_hi = q0 + g + 8;
+        if (rd == 0 && nchunks == 1) {                            // the usual case (n <= CH): K / V in flight while this warp's rows are fetched
+            load_slice_skew_async<HD>(As, base, ld, E + h * HD, 0, n);
+            load_slice_skew_async<HD>(Bs, base, ld, 2 * E + h * HD, 0, n);
+            cp_async_commit();
+        }
         float qa[HD / 8][4], ga[HD / 8][4];                       // contraction slots relabelled by pi (see the forward)
-        load_afrag_pi<HD>(qa, base, ld, h * HD, q0, n, scale * LOG2E, g, t);
+        load_afrag_pi<HD>(qa, base, ld, h * HD, q0, n, scale * LOG2E * TRUNC1, g, t);      // TRUNC1: K / V arrive as raw bits and are truncated by the MMA
         // dO rows once: the A fragments of dP = dO V^T and, against the matching share of O, D = dO . O (each lane of the quad holds
         // HD/4 of the dims)
         float D_lo = 0.f, D_hi = 0.f, L_lo = INFINITY, L_hi = INFINITY;
@@ -485,7 +538,7 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
             float g_lo[HD / 4], g_hi[HD / 4], o_lo[HD / 4], o_hi[HD / 4];
             load_rows_pi<HD>(g_lo, g_hi, gbase, (size_t)E, 0, q0, n, g, t);
             load_rows_pi<HD>(o_lo, o_hi, obase, (size_t)E, 0, q0, n, g, t);
-            afrag_from_rows<HD>(ga, g_lo, g_hi, 1.0f);
+            afrag_from_rows<HD>(ga, g_lo, g_hi, TRUNC1);
 #pragma unroll
             for (int d = 0; d < HD / 4; ++d) { D_lo = fmaf(g_lo[d], o_lo[d], D_lo); D_hi = fmaf(g_hi[d], o_hi[d], D_hi); }
         }
@@ -498,10 +551,15 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
 
         for (int c = 0; c < nchunks; ++c) {
             const int k0c = c * CH, kn = min(CH, n - k0c);
-            if (nchunks > 1 || rd == 0) {
+            if (nchunks > 1) {
                 __syncthreads();
-                load_slice_skew<HD>(As, base, ld, E + h * HD, k0c, kn, 1.0f);
-                load_slice_skew<HD>(Bs, base, ld, 2 * E + h * HD, k0c, kn, 1.0f);
+                load_slice_skew_async<HD>(As, base, ld, E + h * HD, k0c, kn);
+                load_slice_skew_async<HD>(Bs, base, ld, 2 * E + h * HD, k0c, kn);
+                cp_async_commit();
+                cp_async_wait_all();
+                __syncthreads();
+            } else if (rd == 0) {
+                cp_async_wait_all();
                 __syncthreads();
             }
             if (!active) continue;
@@ -537,7 +595,7 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
             }
         }
         if (!active) continue;
-        store_sigma<HD>(dqkv + (size_t)(r0 + q_lo) * ld + h * HD, dqkv + (size_t)(r0 + q_hi) * ld + h * HD, dq, scale * TRUNC1, q_lo < n, q_hi < n, t);
+        store_sigma<HD>(dqkv + (size_t)(r0 + q_lo) * ld + h * HD, dqkv + (size_t)(r0 + q_hi) * ld + h * HD, dq, scale * TRUNC1 * TRUNC1, q_lo < n, q_hi < n, t);      // dS and K both truncated
     }
 
     // ---- phase 2: dV_j = sum_i P_ij dO_i ; dK_j = scale * sum_i dS_ij Q_i ; warp owns 16 keys -----------------
@@ -545,8 +603,8 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
         const int k0 = rd * 64 + warp * 16;
         const bool active = k0 < n;
         float ka[HD / 8][4], va[HD / 8][4];
-        load_afrag_pi<HD>(ka, base, ld, E + h * HD, k0, n, scale * LOG2E, g, t);
-        load_afrag_pi<HD>(va, base, ld, 2 * E + h * HD, k0, n, 1.0f, g, t);
+        load_afrag_pi<HD>(ka, base, ld, E + h * HD, k0, n, scale * LOG2E * TRUNC1, g, t);      // TRUNC1: Q / dO arrive as raw bits
+        load_afrag_pi<HD>(va, base, ld, 2 * E + h * HD, k0, n, TRUNC1, g, t);
         float dk[HD / 8][4], dv[HD / 8][4];
 #pragma unroll
         for (int i = 0; i < HD / 8; ++i) { dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; }
@@ -555,8 +613,9 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
             const int q0c = c * CH, qn = min(CH, n - q0c);
             if (nchunks > 1 || rd == 0) {
                 __syncthreads();                    // also orders phase-1 readers of As/Bs before the overwrite
-                load_slice_skew<HD>(As, base, ld, h * HD, q0c, qn, 1.0f);
-                load_slice_skew<HD>(Bs, gbase, (size_t)E, 0, q0c, qn, 1.0f);
+                load_slice_skew_async<HD>(As, base, ld, h * HD, q0c, qn);
+                load_slice_skew_async<HD>(Bs, gbase, (size_t)E, 0, q0c, qn);
+                cp_async_commit();
                 const int pad = (qn + 7) & ~7;
                 for (int i = threadIdx.x; i < pad; i += ATC_THREADS) {
                     float Di = 0.f, Li = INFINITY;                      // stored negated: accumulator initial values of the tile loop
@@ -571,6 +630,7 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
                     }
                     D_s[i] = -Di; lse_s[i] = -Li;
                 }
+                cp_async_wait_all();
                 __syncthreads();
             }
             if (!active) continue;
@@ -616,8 +676,8 @@ __global__ void __launch_bounds__(ATC_THREADS) attn_bwd_mma_kernel(const float* 
         const int k_lo = k0 + g, k_hi = k0 + g + 8;
         float* row_lo = dqkv + (size_t)(r0 + k_lo) * ld + h * HD;
         float* row_hi = dqkv + (size_t)(r0 + k_hi) * ld + h * HD;
-        store_sigma<HD>(row_lo + E, row_hi + E, dk, scale * TRUNC1, k_lo < n, k_hi < n, t);
-        store_sigma<HD>(row_lo + 2 * E, row_hi + 2 * E, dv, TRUNC1, k_lo < n, k_hi < n, t);
+        store_sigma<HD>(row_lo + E, row_hi + E, dk, scale * TRUNC1 * TRUNC1, k_lo < n, k_hi < n, t);       // dS / P and Q / dO all truncated
+        store_sigma<HD>(row_lo + 2 * E, row_hi + 2 * E, dv, TRUNC1 * TRUNC1, k_lo < n, k_hi < n, t);
     }
 }
 
