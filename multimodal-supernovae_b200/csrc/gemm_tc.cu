@@ -156,10 +156,18 @@ __device__ __forceinline__ void box_row_read(const uint8_t* box, int r, float* v
 // LN_CH: 0 = plain epilogue; 1 or 2 = residual+LayerNorm epilogue over N = 32*LN_CH columns.
 // The aux tile (residual `addend` or ReLU-mask source `act_src`, same [M,N] shape as C) is streamed by its own TMA producer
 // into the aux ring, so its HBM latency is hidden exactly like the A operand's.
-template <int LN_CH>
-__global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapX,
+// EG: epilogue warp groups.  EG == 2 (plain epilogue, no aux stream): a second group of four warps (TMEM lane access goes by
+// warp % 4, so warps 7..10 reach the same quadrants) takes every other tile -- group g always drains accumulator buffer g -- so two
+// warps per scheduler work on the output side.  The single group was the measured bottleneck of this kernel (one thread per row,
+// ~1450 cycles per 32-column chunk, producer and MMA warps idle: profiles/r01_gemm_epilogue_sampling.md).  The groups share no
+// state: each has its own TMEM buffer, accumulator barriers and store boxes (the second group's boxes take the last two ring
+// slots, the A ring runs with five).
+template <int LN_CH, int EG = 1>
+__global__ void __launch_bounds__(32 * (EPI_WARP0 + NUM_EPI_WARPS * EG), 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapX,
                                                               const __grid_constant__ CUtensorMap tmapC, const __grid_constant__ CUtensorMap tmapH,
                                                               const TcArgs a) {
+    constexpr int NT = 32 * (EPI_WARP0 + NUM_EPI_WARPS * EG);
+    static_assert(EG == 1 || LN_CH == 0, "two epilogue groups: plain epilogue only");
     extern __shared__ uint8_t smem_raw[];
     pdl_trigger();
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -196,16 +204,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
     {
         constexpr int UN = 8;
         const int nvec = (N * K) >> 2;
-        for (int i0 = threadIdx.x; i0 < nvec; i0 += NTHREADS * UN) {
+        for (int i0 = threadIdx.x; i0 < nvec; i0 += NT * UN) {
             float4 w[UN];
 #pragma unroll
             for (int u = 0; u < UN; ++u) {
-                const int i = i0 + u * NTHREADS;
+                const int i = i0 + u * NT;
                 w[u] = i < nvec ? __ldg(reinterpret_cast<const float4*>(a.B) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int u = 0; u < UN; ++u) {
-                const int i = i0 + u * NTHREADS;
+                const int i = i0 + u * NT;
                 if (i >= nvec) break;
                 if (a.b_is_nk) {         // B[n][k], k contiguous: 4 consecutive k of one row n -> one 16-byte chunk
                     const int n = i / (K >> 2), k = (i % (K >> 2)) << 2;
@@ -222,9 +230,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
             }
         }
     }
-    for (int i = threadIdx.x; i < N; i += NTHREADS) vec[i] = a.ep.bias ? a.ep.bias[i] : 0.f;
+    for (int i = threadIdx.x; i < N; i += NT) vec[i] = a.ep.bias ? a.ep.bias[i] : 0.f;
     if (LN_CH > 0) {
-        for (int i = threadIdx.x; i < N; i += NTHREADS) { vec[256 + i] = a.ep.gamma[i]; vec[320 + i] = a.ep.beta[i]; }
+        for (int i = threadIdx.x; i < N; i += NT) { vec[256 + i] = a.ep.gamma[i]; vec[320 + i] = a.ep.beta[i]; }
     }
     fence_proxy_async();
     tc_fence_before();
@@ -315,7 +323,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
         // One 32-column chunk of this warp's 32 output rows: the lanes write their rows into one of the warp's two private
         // [32 x 32 fp32] swizzled boxes, then lane 0 issues a TMA store of the box (full tiles) or the warp stores the rows
         // with a predicate (the last, partial tile).  No cross-warp synchronisation: each warp owns its bulk groups.
-        uint8_t* mybox = smem + OFF_OUT + (warp - EPI_WARP0) * 2 * WBOX_BYTES;
+        const int grp = (warp - EPI_WARP0) / NUM_EPI_WARPS;          // 0, or 1 for the second group (EG == 2)
+        uint8_t* mybox = grp == 0 ? smem + OFF_OUT + (warp - EPI_WARP0) * 2 * WBOX_BYTES
+                                  : smem + OFF_A + (NSTAGE - 2) * STAGE_BYTES + (warp - EPI_WARP0 - NUM_EPI_WARPS) * 2 * WBOX_BYTES;
         auto put_chunk = [&](const CUtensorMap* tmap, float* gdst, const float* v, int tile, int c0, bool full_tile) {
             uint8_t* box = mybox + (oit & 1) * WBOX_BYTES;
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the store issued from this box two chunks ago has read it
@@ -334,7 +344,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
             }
             ++oit;
         };
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tc_i) {
+        tc_i = grp;
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < ntiles; tile += EG * gridDim.x, tc_i += EG) {
             const int buf = tc_i & 1;
             mbar_wait(tfull_bar(buf), (tc_i >> 1) & 1);
             tc_fence_after();
@@ -438,22 +449,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_gemm_kernel(const __grid_const
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int LN_CH>
+template <int LN_CH, int EG = 1>
 int launch_tc(const CUtensorMap& tm, const CUtensorMap& tx, const CUtensorMap& tcm, const CUtensorMap& thm, const TcArgs& a, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        MVN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<LN_CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        MVN_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<LN_CH, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         configured = true;
     }
     const int tiles = cdiv(a.M_cap, TILE_M);
     const int grid = tiles < num_sms() ? tiles : num_sms();
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(32 * (EPI_WARP0 + NUM_EPI_WARPS * EG)); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    MVN_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<LN_CH>, tm, tx, tcm, thm, a));
+    MVN_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel<LN_CH, EG>, tm, tx, tcm, thm, a));
     MVN_LAUNCH_CHECK();
     return 0;
 }
@@ -676,6 +687,11 @@ int launch_gemm_tc(const float* A, const float* Bm, float* C, const int32_t* n_r
     const CUtensorMap* tcm = get_tmap_2d(C, M_cap, N, 32, false);                    // per-warp [32 x 32] store boxes
     const CUtensorMap* thm = (ln && ep.xhat) ? get_tmap_2d(ep.xhat, M_cap, N, 32, false) : tcm;
     if (!tcm || !thm) return MVN_E_BADARG;
+    static const int eg = getenv("MVN_GEMM_EG") ? atoi(getenv("MVN_GEMM_EG")) : 2;       // MVN_GEMM_EG=1: single epilogue group (A/B)
+    if (!ln && !aux && eg == 2) {
+        a.nA = NSTAGE - 2;                                                                // the second group's store boxes live in the last two slots
+        return launch_tc<0, 2>(*tm, *tx, *tcm, *thm, a, st);
+    }
     if (!ln) return launch_tc<0>(*tm, *tx, *tcm, *thm, a, st);
     return N == 32 ? launch_tc<1>(*tm, *tx, *tcm, *thm, a, st) : launch_tc<2>(*tm, *tx, *tcm, *thm, a, st);
 }
