@@ -57,6 +57,9 @@ void        mvn_tier_reset(void);
  * that class is bracketed by CUDA events on its own stream; mvn_prof_read sums and clears them.
  * classes: 0 GEMM (fwd + input-grad), 1 weight-grad GEMM, 2 attention fwd, 3 attention bwd, 4 row kernels
  * (embed/LN-bwd/pool/reduce), 5 CLIP loss, 6 optimizer, 7 ConvMixer. */
+/* Programmatic dependent launch of the persistent kernels on (default) / off; the environment variable MVN_PDL overrides.  Host
+ * policy (models_multimodal.py): off when two sequence-encoder chains run concurrently on two streams. */
+void        mvn_set_pdl(int on);
 void        mvn_prof_enable(unsigned class_mask);
 int         mvn_prof_read(int cls, double* total_ms, long long* count);
 

@@ -34,6 +34,7 @@ _SIGS = {
     "mvn_launch_count": (ctypes.c_longlong, []),
     "mvn_tier_count": (ctypes.c_longlong, [c_int]),
     "mvn_tier_reset": (None, []),
+    "mvn_set_pdl": (None, [c_int]),
     "mvn_prof_enable": (None, [ctypes.c_uint]),
     "mvn_prof_read": (c_int, [c_int, POINTER(c_double), POINTER(ctypes.c_longlong)]),
     "mvn_pack_plan": (c_int, [P, c_int, c_int, c_int, P, P, P, P]),

@@ -23,11 +23,22 @@ int num_sms() {
     }
     return cached;
 }
-bool pdl_enabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("MVN_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
-    return v == 1;
+// Programmatic dependent launch: env MVN_PDL=0/1 pins it; otherwise the host chooses per model with mvn_set_pdl().  Measured on
+// B200: a single chain of kernels (C2, and C3 where the ConvMixer chain is short) gains 3 - 4 % from dependents whose prologue runs
+// under the predecessor's tail; with two long encoder chains on two streams (C4 / C5) the early-scheduled CTAs hold SM slots the
+// other chain's kernels would have used, and the step is 1.5 - 3 % SLOWER -- so the model switches it off there.
+static int g_pdl = -1;      // -1: not chosen yet (default on)
+static int pdl_env() {
+    static int v = -2;
+    if (v == -2) { const char* e = getenv("MVN_PDL"); v = !e ? -1 : (e[0] == '0' ? 0 : 1); }
+    return v;
 }
+bool pdl_enabled() {
+    const int e = pdl_env();
+    if (e >= 0) return e == 1;
+    return g_pdl != 0;
+}
+extern "C" void mvn_set_pdl(int on) { g_pdl = on ? 1 : 0; }
 static const uint32_t* g_step_ctr = nullptr;
 const uint32_t* step_counter() { return g_step_ctr; }
 static long long g_launches = 0;

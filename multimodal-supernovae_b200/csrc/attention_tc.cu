@@ -292,6 +292,7 @@ template <int HD>
 __global__ void __launch_bounds__(ATC_THREADS) attn_fwd_mma_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ cu,
                                                                    float* __restrict__ out, float* __restrict__ lse, int E, int H, float scale) {
     pdl_trigger();
+    pdl_wait();                                  // launched as a programmatic dependent: nothing above touches global memory
     constexpr int LD = HD + 4, KS = HD / 8;
     __shared__ __align__(16) float Ks[CH * LD];
     __shared__ __align__(16) float Vs[CH * LD];
@@ -432,6 +433,7 @@ template <int HD>
 __global__ void __launch_bounds__(ATC_THREADS) attn_fwd_mma2_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ cu,
                                                                     float* __restrict__ out, float* __restrict__ lse, int E, int H, float scale) {
     pdl_trigger();
+    pdl_wait();                                  // launched as a programmatic dependent: nothing above touches global memory
     constexpr int LD = HD + 4, KS = HD / 8, MQ = 2, RQ = 64 * MQ;          // queries per round
     __shared__ __align__(16) float Ks[CH * HD];
     __shared__ __align__(16) float Vs[CH * LD];
@@ -497,6 +499,7 @@ __global__ void __launch_bounds__(ATC_THREADS, HD == 16 ? 6 : 0) attn_bwd_mma_ke
                                                                    const float* __restrict__ dout, float* __restrict__ dqkv,
                                                                    int E, int H, float scale) {
     pdl_trigger();
+    pdl_wait();                                  // launched as a programmatic dependent: nothing above touches global memory
     __shared__ __align__(16) float As[skew_floats<HD>(CH)];     // phase 1: K        phase 2: Q      (skewed rows: rowoff<HD>)
     __shared__ __align__(16) float Bs[skew_floats<HD>(CH)];     // phase 1: V        phase 2: dO
     __shared__ __align__(8) float lse_s[CH];        // phase 2: -lse_i * log2e (-inf on padding rows)
@@ -693,8 +696,8 @@ int launch_attention_fwd_tc(const float* qkv, const int32_t* cu, float* out, flo
     static const int variant = getenv("MVN_ATTN_FWD") ? atoi(getenv("MVN_ATTN_FWD")) : 1;
     if (variant == 2 && hd == 8) attn_fwd_mma2_kernel<8><<<B * H, ATC_THREADS, 0, st>>>(qkv, cu, out, lse, E, H, scale);
     else if (variant == 2 && hd == 16) attn_fwd_mma2_kernel<16><<<B * H, ATC_THREADS, 0, st>>>(qkv, cu, out, lse, E, H, scale);
-    else if (hd == 8) attn_fwd_mma_kernel<8><<<B * H, ATC_THREADS, 0, st>>>(qkv, cu, out, lse, E, H, scale);
-    else if (hd == 16) attn_fwd_mma_kernel<16><<<B * H, ATC_THREADS, 0, st>>>(qkv, cu, out, lse, E, H, scale);
+    else if (hd == 8) MVN_CUDA(launch_dependent(attn_fwd_mma_kernel<8>, dim3(B * H), dim3(ATC_THREADS), 0, st, qkv, cu, out, lse, E, H, scale));
+    else if (hd == 16) MVN_CUDA(launch_dependent(attn_fwd_mma_kernel<16>, dim3(B * H), dim3(ATC_THREADS), 0, st, qkv, cu, out, lse, E, H, scale));
     else return MVN_E_UNSUPPORTED;
     MVN_LAUNCH_CHECK();
     return 0;
@@ -702,8 +705,8 @@ int launch_attention_fwd_tc(const float* qkv, const int32_t* cu, float* out, flo
 int launch_attention_bwd_tc(const float* qkv, const int32_t* cu, const float* out, const float* lse, const float* dout, float* dqkv,
                             int B, int E, int H, float scale, cudaStream_t st) {
     const int hd = E / H;
-    if (hd == 8) attn_bwd_mma_kernel<8><<<B * H, ATC_THREADS, 0, st>>>(qkv, cu, out, lse, dout, dqkv, E, H, scale);
-    else if (hd == 16) attn_bwd_mma_kernel<16><<<B * H, ATC_THREADS, 0, st>>>(qkv, cu, out, lse, dout, dqkv, E, H, scale);
+    if (hd == 8) MVN_CUDA(launch_dependent(attn_bwd_mma_kernel<8>, dim3(B * H), dim3(ATC_THREADS), 0, st, qkv, cu, out, lse, dout, dqkv, E, H, scale));
+    else if (hd == 16) MVN_CUDA(launch_dependent(attn_bwd_mma_kernel<16>, dim3(B * H), dim3(ATC_THREADS), 0, st, qkv, cu, out, lse, dout, dqkv, E, H, scale));
     else return MVN_E_UNSUPPORTED;
     MVN_LAUNCH_CHECK();
     return 0;

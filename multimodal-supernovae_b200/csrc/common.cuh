@@ -112,6 +112,18 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 bool pdl_enabled();      // env MVN_PDL=0 switches the attribute off (A/B measurements)
+// Launch `k` as a programmatic dependent of its predecessor in the stream: its CTAs are scheduled as the predecessor drains (the
+// launch gap and CTA ramp-up overlap the predecessor's tail).  `k` MUST call pdl_wait() before its first global access.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_dependent(void (*k)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k, static_cast<KArgs>(args)...);
+}
 
 // ---- dropout (nn.Dropout in Transformer / TransformerBlock, src/transformer_utils.py:112,115,147) ---------------------
 // Counter-based: the keep/drop decision of element `idx` at dropout site `site` is a pure function of (seed, site, idx),

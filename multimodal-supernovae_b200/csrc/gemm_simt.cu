@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
                                                               int nslabs, float* __restrict__ out, int accumulate) {
     __shared__ float red[8][33];
     pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t i = (size_t)blockIdx.x * 32 + lane;
     float acc = 0.f;
@@ -351,7 +352,7 @@ int launch_reduce_partials_n(const float* partial, size_t pstride, size_t n, int
     if (n == 0) return 0;
     ProfScope prof(PROF_ROW, st);
     const int blocks = (int)((n + 31) / 32);
-    reduce_partials_kernel<<<blocks, 256, 0, st>>>(partial, pstride, n, nslabs, out, accumulate);
+    MVN_CUDA(launch_dependent(reduce_partials_kernel, dim3(blocks), dim3(256), 0, st, partial, pstride, n, nslabs, out, accumulate));
     MVN_LAUNCH_CHECK();
     return 0;
 }

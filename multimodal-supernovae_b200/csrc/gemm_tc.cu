@@ -363,8 +363,13 @@ __global__ void __launch_bounds__(32 * (EPI_WARP0 + NUM_EPI_WARPS * EG), 1) tc_g
                     } else {
                         tmem_ld32(taddr + c0, v);
                     }
+                    if (ep.bias) {                               // q/k/v projections and every input-gradient GEMM have none: 32 LDS + 32 FADD per chunk less
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] += vec[(c0 + j) & 255];
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(vec + ((c0 + j) & 255));
+                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                        }
+                    }
                     if (ep.addend) {
                         float r[32];
                         aux_row(r);
@@ -397,7 +402,10 @@ __global__ void __launch_bounds__(32 * (EPI_WARP0 + NUM_EPI_WARPS * EG), 1) tc_g
                 for (int c = 0; c < LN_CH; ++c) {
                     tmem_ld32(taddr + c * 32, v[c]);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[c][j] += vec[c * 32 + j];
+                    for (int j = 0; j < 32; j += 4) {          // broadcast 128-bit loads (OFF_VEC is 16-byte aligned)
+                        const float4 b4 = *reinterpret_cast<const float4*>(vec + c * 32 + j);
+                        v[c][j] += b4.x; v[c][j + 1] += b4.y; v[c][j + 2] += b4.z; v[c][j + 3] += b4.w;
+                    }
                     if (ep.addend) {
                         float r[32];
                         aux_row(r);
@@ -425,7 +433,11 @@ __global__ void __launch_bounds__(32 * (EPI_WARP0 + NUM_EPI_WARPS * EG), 1) tc_g
                     for (int j = 0; j < 32; ++j) v[c][j] *= rs;
                     if (ep.xhat) put_chunk(&tmapH, ep.xhat, v[c], tile, c * 32, full_tile);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[c][j] = fmaf(v[c][j], vec[256 + c * 32 + j], vec[320 + c * 32 + j]);
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 g4 = *reinterpret_cast<const float4*>(vec + 256 + c * 32 + j), b4 = *reinterpret_cast<const float4*>(vec + 320 + c * 32 + j);
+                        v[c][j] = fmaf(v[c][j], g4.x, b4.x); v[c][j + 1] = fmaf(v[c][j + 1], g4.y, b4.y);
+                        v[c][j + 2] = fmaf(v[c][j + 2], g4.z, b4.z); v[c][j + 3] = fmaf(v[c][j + 3], g4.w, b4.w);
+                    }
                     if (ep.drop.thresh) {
                         const uint32_t rk = drop_rowkey(ep.drop, (uint32_t)(row0 + lane));
 #pragma unroll

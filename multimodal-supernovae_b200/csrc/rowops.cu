@@ -272,6 +272,7 @@ __global__ void __launch_bounds__(LNB_WARPS * 32) ln_bwd_vec_kernel(const float*
     constexpr int RPW = 32 / LPR, E = LPR * 4;
     __shared__ float red[LNB_WARPS][32][8];
     pdl_trigger();
+    pdl_wait();
     const int rows = n_rows_dev ? min(*n_rows_dev, M_cap) : M_cap;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int sub = lane / LPR, cl = lane % LPR;
@@ -441,10 +442,10 @@ int launch_ln_bwd(const float* dY, const float* xhat, const float* rstd, const f
     ProfScope prof(PROF_ROW, st);
     if (aligned16(dY) && aligned16(xhat) && aligned16(dZ) && aligned16(gamma) && (E == 16 || E == 32 || E == 64 || E == 128)) {
         switch (E) {
-            case 16: ln_bwd_vec_kernel<4, 4><<<kSlabs, LNB_WARPS * 32, 0, st>>>(dY, xhat, rstd, gamma, dZ, n_rows_dev, M_cap, partial, pstride, goff, boff, drop); break;
-            case 32: ln_bwd_vec_kernel<8, 4><<<kSlabs, LNB_WARPS * 32, 0, st>>>(dY, xhat, rstd, gamma, dZ, n_rows_dev, M_cap, partial, pstride, goff, boff, drop); break;
-            case 64: ln_bwd_vec_kernel<16, 4><<<kSlabs, LNB_WARPS * 32, 0, st>>>(dY, xhat, rstd, gamma, dZ, n_rows_dev, M_cap, partial, pstride, goff, boff, drop); break;
-            default: ln_bwd_vec_kernel<32, 4><<<kSlabs, LNB_WARPS * 32, 0, st>>>(dY, xhat, rstd, gamma, dZ, n_rows_dev, M_cap, partial, pstride, goff, boff, drop); break;
+            case 16: MVN_CUDA(launch_dependent(ln_bwd_vec_kernel<4, 4>, dim3(kSlabs), dim3(LNB_WARPS * 32), 0, st, dY, xhat, rstd, gamma, dZ, n_rows_dev, M_cap, partial, pstride, goff, boff, drop)); break;
+            case 32: MVN_CUDA(launch_dependent(ln_bwd_vec_kernel<8, 4>, dim3(kSlabs), dim3(LNB_WARPS * 32), 0, st, dY, xhat, rstd, gamma, dZ, n_rows_dev, M_cap, partial, pstride, goff, boff, drop)); break;
+            case 64: MVN_CUDA(launch_dependent(ln_bwd_vec_kernel<16, 4>, dim3(kSlabs), dim3(LNB_WARPS * 32), 0, st, dY, xhat, rstd, gamma, dZ, n_rows_dev, M_cap, partial, pstride, goff, boff, drop)); break;
+            default: MVN_CUDA(launch_dependent(ln_bwd_vec_kernel<32, 4>, dim3(kSlabs), dim3(LNB_WARPS * 32), 0, st, dY, xhat, rstd, gamma, dZ, n_rows_dev, M_cap, partial, pstride, goff, boff, drop)); break;
         }
         MVN_LAUNCH_CHECK();
         return 0;

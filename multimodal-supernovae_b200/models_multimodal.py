@@ -309,7 +309,12 @@ class LightCurveImageCLIP(_Base):
         launch / prologue / tail gaps leave the SMs idle.  Enqueue every encoder on its own stream so the block scheduler
         fills one chain's gaps with the other chain's CTAs; autograd replays each encoder's backward on the stream its
         forward ran on, so the backward chains interleave the same way.  Outputs are joined on the caller's stream."""
-        if not (self.concurrent_modalities and len(jobs) > 1 and dev.type == "cuda"):
+        concurrent = self.concurrent_modalities and len(jobs) > 1 and dev.type == "cuda"
+        # programmatic dependent launches help one kernel chain and hurt two long concurrent ones (measured, csrc/api.cu): off when
+        # both sequence encoders run side by side
+        n_seq = ("lightcurve" in self.combinations) + ("spectral" in self.combinations)
+        _lib.lib().mvn_set_pdl(0 if (concurrent and n_seq >= 2) else 1)
+        if not concurrent:
             return [j() for j in jobs]
         main = torch.cuda.current_stream(dev)
         side = _SIDE_STREAMS.setdefault(dev.index if dev.index is not None else torch.cuda.current_device(), [])
