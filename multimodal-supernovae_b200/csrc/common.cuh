@@ -1,5 +1,6 @@
 // Shared helpers for libmaven_sm100.so (sm_100a only).
 #pragma once
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -112,8 +113,11 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 bool pdl_enabled();      // env MVN_PDL=0 switches the attribute off (A/B measurements)
-// Launch `k` as a programmatic dependent of its predecessor in the stream: its CTAs are scheduled as the predecessor drains (the
-// launch gap and CTA ramp-up overlap the predecessor's tail).  `k` MUST call pdl_wait() before its first global access.
+// Launch `k` as a programmatic dependent of its predecessor in the stream when MVN_PDL_NEW=1 (its CTAs are scheduled as the
+// predecessor drains); a plain launch otherwise.  `k` MUST call pdl_wait() before its first global access.  Used by the attention,
+// LayerNorm-backward and partial-reduction kernels.  Measured on B200 (bench.py, CUDA-graph replay): making these kernels dependents
+// changed C2 by -0.7 %, C3 by 0 % and C4 / C5 run with dependents off altogether (api.cu), so the attribute is OFF by default here --
+// only the tcgen05 GEMM / fused feed-forward kernels, whose weight-staging prologue is long, launch as dependents.
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_dependent(void (*k)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg = {};
@@ -121,7 +125,8 @@ inline cudaError_t launch_dependent(void (*k)(KArgs...), dim3 grid, dim3 block, 
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    static const bool on = getenv("MVN_PDL_NEW") && getenv("MVN_PDL_NEW")[0] == '1';
+    cfg.attrs = at; cfg.numAttrs = (on && pdl_enabled()) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, k, static_cast<KArgs>(args)...);
 }
 

@@ -1,0 +1,7 @@
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+nvidia-smi -L | head -3
+timeout 600 python -m pytest tests/test_gpu_fullmodel.py -q -k "data_parallel" 2>&1 | tail -3 | cut -c1-300
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r28_bench_c4_2gpu.json 2> gpurun_out/r28_bench_c4_2gpu.err; tail -2 gpurun_out/r28_bench_c4_2gpu.err | cut -c1-300
+python -c "
+import json; d=json.load(open('gpurun_out/r28_bench_c4_2gpu.json')); print('c4 2gpu', round(d['value']), round(d['ms_per_step'],3), round(d['e2e']['value'])); print(json.dumps(d.get('c5_sweep'))[:900])"

@@ -1,0 +1,32 @@
+# Final measurement pass of the round (second session) on one B200: GPU test suite, smoke, bench lines for every workload, the
+# reference arm, kernel micro-benchmarks, the ncu launch lists of one eager step (C4 and C3) and `--set full` captures of every
+# kernel class (summarised on the CPU box by scripts/ncu_summary.py into profiles/).
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+T=r02b_final
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv | tail -1
+timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/${T}_pytest_gpu.log 2>&1; tail -4 gpurun_out/${T}_pytest_gpu.log | cut -c1-300
+timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2>&1; tail -3 gpurun_out/${T}_smoke.log | cut -c1-300
+timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${T}_bench_c4.json 2> gpurun_out/${T}_bench_c4.err; tail -2 gpurun_out/${T}_bench_c4.err | cut -c1-300
+for wl in c3 c5 c2; do
+timeout 400 python bench.py --steps 20 --warmup 5 --workload $wl --no-cpu-baseline --no-sweep > gpurun_out/${T}_bench_$wl.json 2> gpurun_out/${T}_bench_$wl.err; tail -2 gpurun_out/${T}_bench_$wl.err | cut -c1-300
+done
+timeout 400 python bench.py --steps 20 --warmup 5 --precision tf32 --no-cpu-baseline --no-sweep > gpurun_out/${T}_bench_c4_tf32_unfused.json 2> /dev/null
+timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${T}_reference_arm.json 2> gpurun_out/${T}_reference_arm.err; tail -2 gpurun_out/${T}_reference_arm.err | cut -c1-300
+for f in c4 c3 c5 c2 c4_tf32_unfused; do python -c "
+import json; d=json.load(open('gpurun_out/${T}_bench_$f.json')); r=d['roofline']; print('$f', round(d['value']), 'samples/s', round(d['ms_per_step'],3), 'ms; e2e', round(d['e2e']['value']), '; top', r['kernel_class'], round(r['frac'],4), '; step frac padded', round(r['step_frac_of_tensor_peak']['padded'],4), '; GB/step', round(d['bytes_per_step']['total']/1e9,2))"; done
+python -c "
+import json; d=json.load(open('gpurun_out/${T}_bench_c4.json')); print(d.get('cpu_baseline')); print(d.get('reference_eager_b200')); print(json.dumps(d.get('c5_sweep'))[:600])
+r=json.load(open('gpurun_out/${T}_reference_arm.json')); print('reference arm', round(r['value'],1), r['cpu_baseline']['sample'][:160])"
+(python scripts/bench_fused.py ffn; python scripts/bench_fused.py attn; python scripts/bench_fused.py loss) > gpurun_out/${T}_fused_microbench.txt 2>&1; cat gpurun_out/${T}_fused_microbench.txt
+# launch lists of one eager step (fused tier): C4 and C3
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-sweep --no-graph > /dev/null 2>&1
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${T}_launches_c3.csv python bench.py --steps 1 --warmup 3 --workload c3 --no-cpu-baseline --no-sweep --no-graph > /dev/null 2>&1
+# --set full captures, two launches per kernel class
+for k in ffn_bwd_kernel ffn_fwd_kernel attn_bwd_mma_kernel attn_fwd_mma_kernel tc_gemm_kernel tc_wgrad_kernel ln_bwd_vec_kernel embed_fwd_kernel tc_lse_kernel tc_grad_kernel; do
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k -s 6 -c 2 -f -o gpurun_out/${T}_$k python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-sweep --no-graph > /dev/null 2>&1
+done
+for k in patch_conv_fwd_kernel patch_conv_wgrad_kernel mixer_fwd_kernel mixer_bwd_kernel; do
+timeout 300 ncu --set full --clock-control none -k regex:$k -s 2 -c 4 -f -o gpurun_out/${T}_$k python bench.py --steps 1 --warmup 3 --workload c3 --no-cpu-baseline --no-sweep --no-graph > /dev/null 2>&1
+done
+ls gpurun_out/${T}_*.ncu-rep | wc -l

@@ -18,7 +18,7 @@ from collections import defaultdict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "ns ": 1e-3}
-CLASS = [("ffn_fwd", "fused_fwd"), ("ffn_bwd", "fused_bwd"), ("tc_lse", "loss"), ("tc_grad", "loss"), ("patch_conv", "conv"), ("dwconv", "conv"),
+CLASS = [("mixer_", "conv"), ("pool_bwd_stats", "conv"), ("attn_pool", "row"), ("masked_mse", "loss"), ("ffn_fwd", "fused_fwd"), ("ffn_bwd", "fused_bwd"), ("tc_lse", "loss"), ("tc_grad", "loss"), ("patch_conv", "conv"), ("dwconv", "conv"),
          ("gelu_stats", "conv"), ("bn_", "conv"), ("tc_wgrad", "wgrad"), ("wgrad_kernel", "wgrad"), ("tc_gemm", "gemm"), ("gemm_kernel", "gemm"), ("attn_fwd", "attn_fwd"),
          ("attn_bwd", "attn_bwd"), ("ln_bwd", "row"), ("reduce_partials", "row"), ("embed", "row"), ("pool", "row"),
          ("lse_dir", "loss"), ("grad_dir", "loss"), ("radam", "optim")]
