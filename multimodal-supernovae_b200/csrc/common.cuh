@@ -190,6 +190,9 @@ int launch_wgrad_partials(const float* dY, const float* X, const int32_t* n_rows
 // out[i] = (accumulate? out[i]:0) + sum_s partial[s*pstride + i], i < n
 int launch_reduce_partials(const float* partial, size_t pstride, size_t n, float* out, int accumulate, cudaStream_t st);
 int launch_reduce_partials_n(const float* partial, size_t pstride, size_t n, int nslabs, float* out, int accumulate, cudaStream_t st);
+// nl independent ranges in one launch: out[l * out_lstride + i] (+)= sum_s partial[s * pstride + l * in_lstride + i], i < n
+int launch_reduce_partials_2d(const float* partial, size_t pstride, size_t n, int nslabs, float* out, int accumulate, int nl, size_t in_lstride,
+                              size_t out_lstride, cudaStream_t st);
 int launch_ln_bwd(const float* dY, const float* xhat, const float* rstd, const float* gamma, float* dZ,
                   const int32_t* n_rows_dev, int M_cap, int E, float* partial, size_t pstride, size_t goff, size_t boff,
                   cudaStream_t st, const DropCfg& drop = DropCfg());     // drop: dY is the gradient AFTER the dropout that followed this LayerNorm
@@ -204,7 +207,7 @@ int launch_ffn_fused_fwd(const float* X, const float* W1, const float* b1, const
 int launch_ffn_fused_bwd(const float* dY, const float* xhat, const float* rstd, const float* X, const float* W1, const float* b1,
                          const float* W2, const float* gamma, float* dX, const int32_t* n_rows_dev, int M_cap, int E, const DropCfg& drop,
                          float* partial, size_t pstride, size_t o_w1, size_t o_b1, size_t o_w2, size_t o_b2, size_t o_g, size_t o_b,
-                         float* partial2, cudaStream_t st);
+                         float* partial2, cudaStream_t st, size_t pstride2 = 0);
 size_t ffn_fused_slab_floats(int E);        // one FFN-only slab of the second slab set (w1 | b1 | w2 | b2 | gamma | beta)
 int ffn_fused_bwd_slab_sets(int E);         // 2 when the backward of this width runs two CTAs per SM
 int launch_embed_fwd(const float* x, const float* t, const int32_t* cu_seqlens, const int32_t* tok_src, const float* div_term,

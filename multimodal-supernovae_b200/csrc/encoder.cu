@@ -100,11 +100,15 @@ Workspace carve(const mvn_seq_cfg& c, void* base) {
     const ParamOff o = param_offsets(c);
     size_t head = (size_t)c.n_out * E + c.n_out + (size_t)c.enc_dim * c.n_out + c.enc_dim;
     size_t emb = (size_t)(2 + c.nband) * E;
-    w.pstride = o.layer_stride;
+    // Weight-gradient partials: a slab holds ALL layers ([slab][layer][parameter]), so the backward reduces every layer's gradients in
+    // one launch at its end (one launch per layer was 18 + 13 small kernels per C4 step on the critical chain); the head / embedding
+    // partials reuse the front of the same slabs before / after the layers.
+    const size_t nl = c.depth > 0 ? (size_t)c.depth : 1;
+    w.pstride = o.layer_stride * nl;
     if (head > w.pstride) w.pstride = head;
     if (emb > w.pstride) w.pstride = emb;
     w.partial = (float*)take((size_t)kSlabs * w.pstride * 4);
-    w.partial2 = (w.fuse_ffn && ffn_fused_bwd_slab_sets(c.E) == 2) ? (float*)take((size_t)kSlabs * ffn_fused_slab_floats(c.E) * 4) : nullptr;
+    w.partial2 = (w.fuse_ffn && ffn_fused_bwd_slab_sets(c.E) == 2) ? (float*)take((size_t)kSlabs * ffn_fused_slab_floats(c.E) * nl * 4) : nullptr;
     // per-layer saved activations
     {
         size_t lb = 0;
@@ -268,40 +272,46 @@ extern "C" int mvn_seq_encoder_bwd(const mvn_seq_cfg* cfg, const float* params, 
         const float* P = params + o.layer0 + (size_t)l * o.layer_stride;
         const LayerBuf lb = w.layer(l);
         const float* xin = l > 0 ? w.layer(l - 1).x2 : w.x0;
+        float* lpart = part + (size_t)l * o.layer_stride;                          // this layer's region inside every slab
+        float* lpart2 = w.partial2 ? w.partial2 + (size_t)l * ffn_fused_slab_floats(E) : nullptr;
         if (fuse_ffn) {
             // norm2 backward + ff.2 / ff.0 input and weight gradients in one kernel; h is recomputed from x1 on chip
             MVN_TRY(launch_ffn_fused_bwd(w.dX, lb.xhat2, lb.rstd2, lb.x1, P + o.w1, P + o.b1, P + o.w2, P + o.g2, w.dA, nrows, M, E,
-                                         make_drop(c.dropout_p, c.seed, 2 + 2 * l), part, ps, o.w1, o.b1, o.w2, o.b2, o.g2, o.b2n, w.partial2, st));
+                                         make_drop(c.dropout_p, c.seed, 2 + 2 * l), lpart, ps, o.w1, o.b1, o.w2, o.b2, o.g2, o.b2n, lpart2, st,
+                                         (size_t)c.depth * ffn_fused_slab_floats(E)));
         } else {
         // norm2 backward: dX (grad of x2) -> dz2 in w.dz
-        MVN_TRY(launch_ln_bwd(w.dX, lb.xhat2, lb.rstd2, P + o.g2, w.dz, nrows, M, E, part, ps, o.g2, o.b2n, st, make_drop(c.dropout_p, c.seed, 2 + 2 * l)));
+        MVN_TRY(launch_ln_bwd(w.dX, lb.xhat2, lb.rstd2, P + o.g2, w.dz, nrows, M, E, lpart, ps, o.g2, o.b2n, st, make_drop(c.dropout_p, c.seed, 2 + 2 * l)));
         // ff.2: dW2 = dz2^T h ; dh = (dz2 W2) * relu'(h)
-        MVN_TRY(launch_wgrad_partials(w.dz, lb.h, nrows, M, E, F, part, ps, o.w2, (long long)o.b2, gp, st));
+        MVN_TRY(launch_wgrad_partials(w.dz, lb.h, nrows, M, E, F, lpart, ps, o.w2, (long long)o.b2, gp, st));
         GemmEpilogue eh;
         eh.act_src = lb.h; eh.dact = 1;
         MVN_TRY(launch_gemm(w.dz, P + o.w2, w.dh, nrows, M, F, E, false, eh, gp, st));
         // ff.0: dW1 = dh^T x1 ; dx1 = dh W1 + dz2 (residual)
-        MVN_TRY(launch_wgrad_partials(w.dh, lb.x1, nrows, M, F, E, part, ps, o.w1, (long long)o.b1, gp, st));
+        MVN_TRY(launch_wgrad_partials(w.dh, lb.x1, nrows, M, F, E, lpart, ps, o.w1, (long long)o.b1, gp, st));
         GemmEpilogue e1;
         e1.addend = w.dz;
         MVN_TRY(launch_gemm(w.dh, P + o.w1, w.dA, nrows, M, E, F, false, e1, gp, st));
         }
         // norm1 backward: dA -> dz1 in w.dz
-        MVN_TRY(launch_ln_bwd(w.dA, lb.xhat1, lb.rstd1, P + o.g1, w.dz, nrows, M, E, part, ps, o.g1, o.b1n, st, make_drop(c.dropout_p, c.seed, 1 + 2 * l)));
+        MVN_TRY(launch_ln_bwd(w.dA, lb.xhat1, lb.rstd1, P + o.g1, w.dz, nrows, M, E, lpart, ps, o.g1, o.b1n, st, make_drop(c.dropout_p, c.seed, 1 + 2 * l)));
         // unifyheads: dWu = dz1^T att ; datt = dz1 Wu  (into w.dA)
-        MVN_TRY(launch_wgrad_partials(w.dz, lb.att, nrows, M, E, E, part, ps, o.wu, (long long)o.bu, gp, st));
+        MVN_TRY(launch_wgrad_partials(w.dz, lb.att, nrows, M, E, E, lpart, ps, o.wu, (long long)o.bu, gp, st));
         GemmEpilogue e2;
         MVN_TRY(launch_gemm(w.dz, P + o.wu, w.dA, nrows, M, E, E, false, e2, gp, st));
         MVN_TRY(mvn_attention_bwd(lb.qkv, w.cu, nullptr, lb.att, lb.lse, w.dA, w.dqkv, c.B, E, c.H, scale, gp, st));
         // q/k/v projections: dWqkv = dqkv^T xin ; dxin = dqkv Wqkv + dz1 (residual) -> w.dX
-        MVN_TRY(launch_wgrad_partials(w.dqkv, xin, nrows, M, 3 * E, E, part, ps, o.wqkv, -1, gp, st));
+        MVN_TRY(launch_wgrad_partials(w.dqkv, xin, nrows, M, 3 * E, E, lpart, ps, o.wqkv, -1, gp, st));
         GemmEpilogue e3;
         e3.addend = w.dz;
         MVN_TRY(launch_gemm(w.dqkv, P + o.wqkv, w.dX, nrows, M, E, 3 * E, false, e3, gp, st));
-        MVN_TRY(launch_reduce_partials(part, ps, o.layer_stride, grads + o.layer0 + (size_t)l * o.layer_stride, 0, st));
-        if (fuse_ffn && w.partial2)       // the second slab set holds the feed-forward gradients of the CTAs >= kSlabs
-            MVN_TRY(launch_reduce_partials(w.partial2, ffn_fused_slab_floats(E), ffn_fused_slab_floats(E),
-                                           grads + o.layer0 + (size_t)l * o.layer_stride + o.w1, 1, st));
+    }
+    if (c.depth > 0) {
+        // every layer's parameter gradients in one reduction, then the second slab set (feed-forward gradients of the CTAs >= kSlabs)
+        MVN_TRY(launch_reduce_partials(part, ps, (size_t)c.depth * o.layer_stride, grads + o.layer0, 0, st));
+        if (fuse_ffn && w.partial2)
+            MVN_TRY(launch_reduce_partials_2d(w.partial2, (size_t)c.depth * ffn_fused_slab_floats(E), ffn_fused_slab_floats(E), kSlabs, grads + o.layer0 + o.w1, 1,
+                                              c.depth, ffn_fused_slab_floats(E), o.layer_stride, st));
     }
     // embedding_mag / band_emb
     MVN_TRY(launch_embed_bwd_partials(x, w.tok_src, w.dX, nrows, M, c.T, E, c.nband, part, ps, 0, st, make_drop(c.dropout_p, c.seed, 0)));

@@ -522,7 +522,7 @@ int launch_ffn_fused_fwd(const float* X, const float* W1, const float* b1, const
 int launch_ffn_fused_bwd(const float* dY, const float* xhat, const float* rstd, const float* X, const float* W1, const float* b1,
                          const float* W2, const float* gamma, float* dX, const int32_t* n_rows_dev, int M_cap, int E, const DropCfg& drop,
                          float* partial, size_t pstride, size_t o_w1, size_t o_b1, size_t o_w2, size_t o_b2, size_t o_g, size_t o_b,
-                         float* partial2, cudaStream_t st) {
+                         float* partial2, cudaStream_t st, size_t pstride2) {
     MVN_CHECK_ARG(dY && xhat && rstd && X && W1 && W2 && gamma && dX && partial && M_cap > 0, "ffn_fused_bwd: null pointer or empty input");
     MVN_CHECK_ARG(ffn_fused_bwd_slab_sets(E) == 1 || partial2, "ffn_fused_bwd: the second slab set is missing");
     MVN_CHECK_ARG(o_b1 == o_w1 + (size_t)4 * E * E && o_w2 == o_b1 + (size_t)4 * E && o_b2 == o_w2 + (size_t)4 * E * E && o_g == o_b2 + E && o_b == o_g + E,
@@ -537,7 +537,7 @@ int launch_ffn_fused_bwd(const float* dY, const float* xhat, const float* rstd, 
     a.dY = dY; a.xhat = xhat; a.rstd = rstd; a.X = X; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.gamma = gamma; a.dX = dX;
     a.n_rows_dev = n_rows_dev; a.M_cap = M_cap; a.drop = drop; a.partial = partial; a.pstride = pstride;
     a.o_w1 = o_w1; a.o_b1 = o_b1; a.o_w2 = o_w2; a.o_b2 = o_b2; a.o_g = o_g; a.o_b = o_b;
-    a.partial2 = partial2; a.pstride2 = ffn_fused_slab_floats(E);
+    a.partial2 = partial2; a.pstride2 = pstride2 ? pstride2 : ffn_fused_slab_floats(E);
     if (E == 64) return launch_bwd_t<64, 16>(a, st);
     return ffn_fused_bwd_slab_sets(E) == 2 ? launch_bwd_t<32, 8>(a, st) : launch_bwd_t<32, 16>(a, st);
 }

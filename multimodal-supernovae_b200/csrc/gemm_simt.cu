@@ -264,10 +264,12 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ dY
 // out[i] = sum over slabs of partial[s][i]: a block owns 32 consecutive columns, its 8 warps split the slabs (16 independent
 // loads in flight per thread), fixed summation order -> deterministic.
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, size_t pstride, size_t n,
-                                                              int nslabs, float* __restrict__ out, int accumulate) {
+                                                              int nslabs, float* __restrict__ out, int accumulate, size_t in_lstride, size_t out_lstride) {
     __shared__ float red[8][33];
     pdl_trigger();
     pdl_wait();
+    partial += (size_t)blockIdx.y * in_lstride;              // blockIdx.y: independent range (a layer)
+    out += (size_t)blockIdx.y * out_lstride;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t i = (size_t)blockIdx.x * 32 + lane;
     float acc = 0.f;
@@ -352,7 +354,16 @@ int launch_reduce_partials_n(const float* partial, size_t pstride, size_t n, int
     if (n == 0) return 0;
     ProfScope prof(PROF_ROW, st);
     const int blocks = (int)((n + 31) / 32);
-    MVN_CUDA(launch_dependent(reduce_partials_kernel, dim3(blocks), dim3(256), 0, st, partial, pstride, n, nslabs, out, accumulate));
+    MVN_CUDA(launch_dependent(reduce_partials_kernel, dim3(blocks), dim3(256), 0, st, partial, pstride, n, nslabs, out, accumulate, (size_t)0, (size_t)0));
+    MVN_LAUNCH_CHECK();
+    return 0;
+}
+int launch_reduce_partials_2d(const float* partial, size_t pstride, size_t n, int nslabs, float* out, int accumulate, int nl, size_t in_lstride,
+                              size_t out_lstride, cudaStream_t st) {
+    if (n == 0 || nl <= 0) return 0;
+    ProfScope prof(PROF_ROW, st);
+    const int blocks = (int)((n + 31) / 32);
+    MVN_CUDA(launch_dependent(reduce_partials_kernel, dim3(blocks, nl), dim3(256), 0, st, partial, pstride, n, nslabs, out, accumulate, in_lstride, out_lstride));
     MVN_LAUNCH_CHECK();
     return 0;
 }
