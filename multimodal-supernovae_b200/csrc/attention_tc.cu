@@ -290,13 +290,14 @@ __device__ __forceinline__ void fwd_block(const float* __restrict__ Ks, const fl
 
 template <int HD>
 __global__ void __launch_bounds__(ATC_THREADS) attn_fwd_mma_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ cu,
-                                                                   float* __restrict__ out, float* __restrict__ lse, int E, int H, float scale) {
+                                                                   float* __restrict__ out, float* __restrict__ lse, int E, int H, float scale,
+                                                                   const int32_t* __restrict__ order) {
     pdl_trigger();
     pdl_wait();                                  // launched as a programmatic dependent: nothing above touches global memory
     constexpr int LD = HD + 4, KS = HD / 8;
     __shared__ __align__(16) float Ks[CH * LD];
     __shared__ __align__(16) float Vs[CH * LD];
-    const int b = blockIdx.x / H, h = blockIdx.x % H;
+    const int b = order ? order[blockIdx.x / H] : blockIdx.x / H, h = blockIdx.x % H;      // order: longest sequences first (see seq_order_kernel)
     const int r0 = cu[b], n = cu[b + 1] - r0;
     if (n <= 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -497,14 +498,14 @@ template <int HD>
 __global__ void __launch_bounds__(ATC_THREADS, HD == 16 ? 6 : 0) attn_bwd_mma_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ cu,
                                                                    const float* __restrict__ out, const float* __restrict__ lse,
                                                                    const float* __restrict__ dout, float* __restrict__ dqkv,
-                                                                   int E, int H, float scale) {
+                                                                   int E, int H, float scale, const int32_t* __restrict__ order) {
     pdl_trigger();
     pdl_wait();                                  // launched as a programmatic dependent: nothing above touches global memory
     __shared__ __align__(16) float As[skew_floats<HD>(CH)];     // phase 1: K        phase 2: Q      (skewed rows: rowoff<HD>)
     __shared__ __align__(16) float Bs[skew_floats<HD>(CH)];     // phase 1: V        phase 2: dO
     __shared__ __align__(8) float lse_s[CH];        // phase 2: -lse_i * log2e (-inf on padding rows)
     __shared__ __align__(8) float D_s[CH];                       // phase 2: -D_i = -dO_i . O_i
-    const int b = blockIdx.x / H, h = blockIdx.x % H;
+    const int b = order ? order[blockIdx.x / H] : blockIdx.x / H, h = blockIdx.x % H;
     const int r0 = cu[b], n = cu[b + 1] - r0;
     if (n <= 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -685,7 +686,34 @@ __global__ void __launch_bounds__(ATC_THREADS, HD == 16 ? 6 : 0) attn_bwd_mma_ke
     }
 }
 
+// order[r] = index of the sequence with the r-th largest token count (ties by index): thread b counts the sequences ahead of it.
+// CTAs are dispatched in blockIdx order, so (sequence, head) work items sorted longest-first fill the last wave with the SHORTEST
+// items -- with ~2.5 waves of very unequal CTAs (spectra: 110..220 tokens, cost ~ n^2) a random order left a tail of up to one long
+// CTA on every launch.
+__global__ void __launch_bounds__(256) seq_order_kernel(const int32_t* __restrict__ cu, int B, int32_t* __restrict__ order) {
+    extern __shared__ int32_t len_s[];
+    for (int i = threadIdx.x; i < B; i += 256) len_s[i] = cu[i + 1] - cu[i];
+    __syncthreads();
+    const int b = blockIdx.x * 256 + threadIdx.x;
+    if (b >= B) return;
+    const int nb = len_s[b];
+    int rank = 0;
+    for (int i = 0; i < B; ++i) rank += (len_s[i] > nb) || (len_s[i] == nb && i < b);
+    order[rank] = b;
+}
+const int32_t* g_order = nullptr;       // set by the encoder around its attention launches (host-side, one training thread per device)
+
 }  // namespace
+
+void set_attention_order(const int32_t* order) { g_order = order; }
+int launch_seq_order(const int32_t* cu, int B, int32_t* order, cudaStream_t st) {
+    if ((size_t)B * 4 > 160 * 1024) return MVN_E_UNSUPPORTED;
+    static bool configured = false;
+    if (!configured) { MVN_CUDA(cudaFuncSetAttribute(seq_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); configured = true; }
+    seq_order_kernel<<<cdiv(B, 256), 256, (size_t)B * 4, st>>>(cu, B, order);
+    MVN_LAUNCH_CHECK();
+    return 0;
+}
 
 // Returns MVN_E_UNSUPPORTED for head dims the MMA kernels are not built for (caller falls back to the fp32 kernel).
 int launch_attention_fwd_tc(const float* qkv, const int32_t* cu, float* out, float* lse, int B, int E, int H, float scale, cudaStream_t st) {
@@ -696,8 +724,8 @@ int launch_attention_fwd_tc(const float* qkv, const int32_t* cu, float* out, flo
     static const int variant = getenv("MVN_ATTN_FWD") ? atoi(getenv("MVN_ATTN_FWD")) : 1;
     if (variant == 2 && hd == 8) attn_fwd_mma2_kernel<8><<<B * H, ATC_THREADS, 0, st>>>(qkv, cu, out, lse, E, H, scale);
     else if (variant == 2 && hd == 16) attn_fwd_mma2_kernel<16><<<B * H, ATC_THREADS, 0, st>>>(qkv, cu, out, lse, E, H, scale);
-    else if (hd == 8) MVN_CUDA(launch_dependent(attn_fwd_mma_kernel<8>, dim3(B * H), dim3(ATC_THREADS), 0, st, qkv, cu, out, lse, E, H, scale));
-    else if (hd == 16) MVN_CUDA(launch_dependent(attn_fwd_mma_kernel<16>, dim3(B * H), dim3(ATC_THREADS), 0, st, qkv, cu, out, lse, E, H, scale));
+    else if (hd == 8) MVN_CUDA(launch_dependent(attn_fwd_mma_kernel<8>, dim3(B * H), dim3(ATC_THREADS), 0, st, qkv, cu, out, lse, E, H, scale, g_order));
+    else if (hd == 16) MVN_CUDA(launch_dependent(attn_fwd_mma_kernel<16>, dim3(B * H), dim3(ATC_THREADS), 0, st, qkv, cu, out, lse, E, H, scale, g_order));
     else return MVN_E_UNSUPPORTED;
     MVN_LAUNCH_CHECK();
     return 0;
@@ -705,8 +733,8 @@ int launch_attention_fwd_tc(const float* qkv, const int32_t* cu, float* out, flo
 int launch_attention_bwd_tc(const float* qkv, const int32_t* cu, const float* out, const float* lse, const float* dout, float* dqkv,
                             int B, int E, int H, float scale, cudaStream_t st) {
     const int hd = E / H;
-    if (hd == 8) MVN_CUDA(launch_dependent(attn_bwd_mma_kernel<8>, dim3(B * H), dim3(ATC_THREADS), 0, st, qkv, cu, out, lse, dout, dqkv, E, H, scale));
-    else if (hd == 16) MVN_CUDA(launch_dependent(attn_bwd_mma_kernel<16>, dim3(B * H), dim3(ATC_THREADS), 0, st, qkv, cu, out, lse, dout, dqkv, E, H, scale));
+    if (hd == 8) MVN_CUDA(launch_dependent(attn_bwd_mma_kernel<8>, dim3(B * H), dim3(ATC_THREADS), 0, st, qkv, cu, out, lse, dout, dqkv, E, H, scale, g_order));
+    else if (hd == 16) MVN_CUDA(launch_dependent(attn_bwd_mma_kernel<16>, dim3(B * H), dim3(ATC_THREADS), 0, st, qkv, cu, out, lse, dout, dqkv, E, H, scale, g_order));
     else return MVN_E_UNSUPPORTED;
     MVN_LAUNCH_CHECK();
     return 0;

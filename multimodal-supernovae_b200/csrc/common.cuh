@@ -189,6 +189,9 @@ int launch_wgrad_partials(const float* dY, const float* X, const int32_t* n_rows
                           float* partial, size_t pstride, size_t woff, long long boff, int prec, cudaStream_t st);
 // out[i] = (accumulate? out[i]:0) + sum_s partial[s*pstride + i], i < n
 int launch_reduce_partials(const float* partial, size_t pstride, size_t n, float* out, int accumulate, cudaStream_t st);
+// attention_tc.cu: work-item order of the tensor-core attention kernels (longest sequence first); nullptr = index order
+void set_attention_order(const int32_t* order);
+int launch_seq_order(const int32_t* cu, int B, int32_t* order, cudaStream_t st);
 int launch_reduce_partials_n(const float* partial, size_t pstride, size_t n, int nslabs, float* out, int accumulate, cudaStream_t st);
 // nl independent ranges in one launch: out[l * out_lstride + i] (+)= sum_s partial[s * pstride + l * in_lstride + i], i < n
 int launch_reduce_partials_2d(const float* partial, size_t pstride, size_t n, int nslabs, float* out, int accumulate, int nl, size_t in_lstride,

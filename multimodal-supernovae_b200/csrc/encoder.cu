@@ -1,6 +1,8 @@
 // Whole sequence encoder (A1-A7): TransformerWithTimeEmbeddings.forward + <modality>_projection + L2 norm,
 // forward and backward, as a fixed launch sequence over one caller-owned workspace.  No host reads of device
 // data: the live token count stays on the device (cu_seqlens[B]), so the sequence is CUDA-graph capturable.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mvn {
@@ -49,7 +51,7 @@ ParamOff param_offsets(const mvn_seq_cfg& c) {
 struct LayerBuf { float *qkv, *att, *lse, *xhat1, *rstd1, *x1, *h, *xhat2, *rstd2, *x2; };
 
 struct Workspace {
-    int32_t *cu, *tok_src; uint8_t* keyvalid;
+    int32_t *cu, *tok_src, *order; uint8_t* keyvalid;
     float* x0;
     float *pooled, *p1, *p2, *ynorm, *norm; int32_t* argmax;
     float *dX, *dA, *dz, *dqkv, *dh, *d_p2, *d_p1, *d_pooled;
@@ -80,6 +82,7 @@ Workspace carve(const mvn_seq_cfg& c, void* base) {
     auto take = [&](size_t bytes) { char* r = p; p += align_up(bytes, 256); return r; };
     w.cu = (int32_t*)take((B + 1) * 4);
     w.tok_src = (int32_t*)take(M * 4);
+    w.order = (int32_t*)take(B * 4);
     w.keyvalid = (uint8_t*)take(M);
     w.x0 = (float*)take(M * E * 4);
     w.pooled = (float*)take(B * E * 4);
@@ -148,6 +151,13 @@ extern "C" size_t mvn_seq_param_count(const mvn_seq_cfg* cfg) {
     return param_offsets(*cfg).total;
 }
 
+// tensor-core attention launches take their (sequence, head) work items longest sequence first (attention_tc.cu::seq_order_kernel);
+// the order is computed once per forward and kept in the workspace for the backward.  MVN_ATTN_ORDER=0: index order (A/B).
+static bool attention_ordered(const mvn_seq_cfg& c) {
+    static const bool lpt = !(getenv("MVN_ATTN_ORDER") && getenv("MVN_ATTN_ORDER")[0] == '0');
+    return lpt && c.prec >= 1 && (size_t)c.B * 4 <= 160 * 1024;
+}
+
 extern "C" size_t mvn_seq_workspace_bytes(const mvn_seq_cfg* cfg) {
     if (check_cfg(cfg) != 0) return 0;
     return carve(*cfg, nullptr).bytes + 256;
@@ -171,6 +181,8 @@ extern "C" int mvn_seq_encoder_fwd(const mvn_seq_cfg* cfg, const float* params, 
     const bool fuse_ffn = c.prec == 2 && ffn_fused_supported(E, c.ff_mult);  // prec 2: h stays on chip (ffn_fused.cu)
 
     MVN_TRY(mvn_pack_plan(mask, c.B, c.T, 1, w.cu, w.tok_src, w.keyvalid, st));
+    const bool ordered = attention_ordered(c);
+    if (ordered) MVN_TRY(launch_seq_order(w.cu, c.B, w.order, st));
     // dropout sites (src/transformer_utils.py:147,112,115): 0 = transformer input, 1+2l = after norm1, 2+2l = after norm2 of layer l
     MVN_TRY(launch_embed_fwd(x, t, w.cu, w.tok_src, div_term, params + o.emb_w, params + o.emb_b, c.nband > 1 ? params + o.band : nullptr,
                              c.B, c.T, E, c.nband, w.x0, st, make_drop(c.dropout_p, c.seed, 0)));
@@ -180,7 +192,10 @@ extern "C" int mvn_seq_encoder_fwd(const mvn_seq_cfg* cfg, const float* params, 
         const LayerBuf lb = w.layer(l);
         GemmEpilogue e0;
         MVN_TRY(launch_gemm(xin, P + o.wqkv, lb.qkv, nrows, M, 3 * E, E, true, e0, gp, st));
-        MVN_TRY(mvn_attention_fwd(lb.qkv, w.cu, nullptr, lb.att, lb.lse, c.B, E, c.H, scale, gp, st));
+        set_attention_order(ordered ? w.order : nullptr);
+        const int ra = mvn_attention_fwd(lb.qkv, w.cu, nullptr, lb.att, lb.lse, c.B, E, c.H, scale, gp, st);
+        set_attention_order(nullptr);
+        MVN_TRY(ra);
         GemmEpilogue e1;
         e1.bias = P + o.bu; e1.addend = xin; e1.gamma = P + o.g1; e1.beta = P + o.b1n; e1.xhat = lb.xhat1; e1.rstd = lb.rstd1; e1.eps = c.ln_eps;
         e1.drop = make_drop(c.dropout_p, c.seed, 1 + 2 * l);
@@ -239,6 +254,7 @@ extern "C" int mvn_seq_encoder_bwd(const mvn_seq_cfg* cfg, const float* params, 
     const float scale = 1.0f / sqrtf((float)E);
     const int gp = c.prec >= 1 ? 1 : 0;
     const bool fuse_ffn = c.prec == 2 && ffn_fused_supported(E, c.ff_mult);
+    const bool ordered = attention_ordered(c);
     float* part = w.partial;
     const size_t ps = w.pstride;
 
@@ -299,7 +315,10 @@ extern "C" int mvn_seq_encoder_bwd(const mvn_seq_cfg* cfg, const float* params, 
         MVN_TRY(launch_wgrad_partials(w.dz, lb.att, nrows, M, E, E, lpart, ps, o.wu, (long long)o.bu, gp, st));
         GemmEpilogue e2;
         MVN_TRY(launch_gemm(w.dz, P + o.wu, w.dA, nrows, M, E, E, false, e2, gp, st));
-        MVN_TRY(mvn_attention_bwd(lb.qkv, w.cu, nullptr, lb.att, lb.lse, w.dA, w.dqkv, c.B, E, c.H, scale, gp, st));
+        set_attention_order(ordered ? w.order : nullptr);
+        const int ra = mvn_attention_bwd(lb.qkv, w.cu, nullptr, lb.att, lb.lse, w.dA, w.dqkv, c.B, E, c.H, scale, gp, st);
+        set_attention_order(nullptr);
+        MVN_TRY(ra);
         // q/k/v projections: dWqkv = dqkv^T xin ; dxin = dqkv Wqkv + dz1 (residual) -> w.dX
         MVN_TRY(launch_wgrad_partials(w.dqkv, xin, nrows, M, 3 * E, E, lpart, ps, o.wqkv, -1, gp, st));
         GemmEpilogue e3;
