@@ -1,6 +1,6 @@
-# Final measurement pass of the round (second session) on one B200: GPU test suite, smoke, bench lines for every workload, the
-# reference arm, kernel micro-benchmarks, the ncu launch lists of one eager step (C4 and C3) and `--set full` captures of every
-# kernel class (summarised on the CPU box by scripts/ncu_summary.py into profiles/).
+# Final measurement pass of the round (second session) on one B200, part 1: GPU test suite, smoke, bench lines for every workload,
+# the reference arm, kernel micro-benchmarks and the ncu launch lists of one eager step (C4 and C3).  Part 2 (run_final2_ncu.sh)
+# takes the `--set full` captures.
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 T=r02b_final
@@ -22,11 +22,3 @@ r=json.load(open('gpurun_out/${T}_reference_arm.json')); print('reference arm', 
 # launch lists of one eager step (fused tier): C4 and C3
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-sweep --no-graph > /dev/null 2>&1
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${T}_launches_c3.csv python bench.py --steps 1 --warmup 3 --workload c3 --no-cpu-baseline --no-sweep --no-graph > /dev/null 2>&1
-# --set full captures, two launches per kernel class
-for k in ffn_bwd_kernel ffn_fwd_kernel attn_bwd_mma_kernel attn_fwd_mma_kernel tc_gemm_kernel tc_wgrad_kernel ln_bwd_vec_kernel embed_fwd_kernel tc_lse_kernel tc_grad_kernel; do
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k -s 6 -c 2 -f -o gpurun_out/${T}_$k python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-sweep --no-graph > /dev/null 2>&1
-done
-for k in patch_conv_fwd_kernel patch_conv_wgrad_kernel mixer_fwd_kernel mixer_bwd_kernel; do
-timeout 300 ncu --set full --clock-control none -k regex:$k -s 2 -c 4 -f -o gpurun_out/${T}_$k python bench.py --steps 1 --warmup 3 --workload c3 --no-cpu-baseline --no-sweep --no-graph > /dev/null 2>&1
-done
-ls gpurun_out/${T}_*.ncu-rep | wc -l

@@ -40,8 +40,12 @@ def main():
     ap.add_argument("--tag", required=True)
     ap.add_argument("--precision", default="tf32")
     ap.add_argument("--head", default="", help="git commit the capture was taken on")
+    ap.add_argument("--append", action="store_true", help="append to profiles/<tag>_ncu_summary.md instead of replacing it")
     a = ap.parse_args()
-    raw = subprocess.run(["ncu", "-i", a.report, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if a.report.endswith(".csv"):          # already exported on the GPU box (`ncu -i rep --page raw --csv`)
+        raw = open(a.report).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", a.report, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     ix = {k: hdr.index(v) for k, v in COLS.items() if v in hdr}
@@ -71,7 +75,10 @@ def main():
                 per_class[cls][1] += n
                 break
     out_md = os.path.join(ROOT, "profiles", a.tag + "_ncu_summary.md")
-    open(out_md, "w").write("\n".join(lines) + "\n")
+    if a.append and os.path.exists(out_md):
+        open(out_md, "a").write("\n".join(lines[6:]) + "\n")
+    else:
+        open(out_md, "w").write("\n".join(lines) + "\n")
     tpath = os.path.join(ROOT, "profiles", "traffic_per_launch.json")
     t = json.load(open(tpath)) if os.path.exists(tpath) else {}
     t.setdefault(a.precision, {})
