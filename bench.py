@@ -499,7 +499,7 @@ def run_gpu(args):
     if args.graph:
         from maven_b200.graph import GraphedTrainStep
         try:
-            graphed = GraphedTrainStep(model, opt, resident, group=dist.group.WORLD if world > 1 else None)
+            graphed = GraphedTrainStep(model, opt, resident, group=dist.group.WORLD if world > 1 else None, double_buffer=not args.no_prefetch)
         except Exception as e:                                 # same kernels, launched eagerly: never a different code path
             graph_note = f"eager launches (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
             print(f"[bench] rank {rank}: {graph_note}", file=sys.stderr, flush=True)
@@ -557,25 +557,44 @@ def run_gpu(args):
     clocks = sampler.stop()            # sampled during the throughput region only: NVML queries perturb the sync-per-step e2e loop
 
     # ---- e2e: pinned host batch -> H2D -> step -> D2H loss, everything inside the timed region -----------
-    def e2e_step():
-        if graphed is not None and img_u8 is not None:
+    # With the graph's second input set (GraphedTrainStep(double_buffer=True)) the upload of batch i+1 is enqueued on the copy stream
+    # before the host reads step i's loss, so it runs under step i's compute -- what DataLoader workers + pinned memory do for the
+    # reference.  Every step still uploads its own batch from pinned host memory and reads its own loss back, inside the timed region.
+    prefetch = graphed is not None and not args.no_prefetch
+    u8_dev = torch.empty_like(img_u8, device=dev) if img_u8 is not None else None
+
+    def host_batch(static):
+        if img_u8 is not None:
             from maven_b200.augment import augment_images
             u8_dev.copy_(img_u8, non_blocking=True)
-            augment_images(u8_dev, None, out=graphed.static[0])                    # uint8 -> fp32/255 on the device
-            return graphed([graphed.static[0]] + pinned[1:]).item()
+            augment_images(u8_dev, None, out=static[0])                            # uint8 -> fp32/255 on the device
+            return [static[0]] + pinned[1:]
+        return pinned
+
+    def e2e_step():
         if graphed is not None:
-            return graphed(pinned).item()                      # pinned host batch -> static device buffers -> replay -> D2H loss
+            return graphed(host_batch(graphed.static)).item()  # pinned host batch -> static device buffers -> replay -> D2H loss
         batch = [None if v is None else v.to(dev, non_blocking=True) for v in pinned]
         return step(batch).item()                              # device->host read of the step's loss
 
-    u8_dev = torch.empty_like(img_u8, device=dev) if img_u8 is not None else None
-    for _ in range(2):                                         # settle the allocator for the per-step input buffers
-        e2e_step()
+    def e2e_loop(n):
+        last = None
+        if not prefetch:
+            for _ in range(n):
+                last = e2e_step()
+            return last
+        graphed.prefetch(host_batch)
+        for i in range(n):
+            loss_t = graphed.step_prefetched()
+            if i + 1 < n:
+                graphed.prefetch(host_batch)                   # next batch's upload overlaps this step
+            last = loss_t.item()
+        return last
+
+    e2e_loop(2)                                                # settle the allocator for the per-step input buffers
     sync()
     t0 = time.perf_counter()
-    last = None
-    for _ in range(args.steps):
-        last = e2e_step()
+    last = e2e_loop(args.steps)
     sync()
     e2e_wall = time.perf_counter() - t0
     gc.enable()
@@ -663,7 +682,8 @@ def run_gpu(args):
                               else (graph_note or "eager launches"),
                     "l2": "256 MiB flush written between timed steps; per-step activation working set is GBs (>> 126 MB L2)",
                     "valid_token_fraction": {"lc": float(host[3].float().mean()), "sp": float(host[6].float().mean()) if host[6] is not None else None}},
-        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps,
+                "input_prefetch": "batch i+1 uploaded on a copy stream while step i runs (GraphedTrainStep double_buffer)" if (graphed is not None and not args.no_prefetch) else "none"},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": ct["bound"], "kernel_class": top, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
@@ -726,6 +746,7 @@ def main():
     ap.add_argument("--no-sweep", dest="sweep", action="store_false", help="skip the C5 large-global-batch sweep that follows the headline measurement")
     ap.add_argument("--sweep-max-per-gpu", type=int, default=8192, help="largest per-GPU batch of the C5 sweep (activation workspace ~5 GB per 1024 samples)")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="enqueue every kernel from Python instead of replaying the captured step")
+    ap.add_argument("--no-prefetch", action="store_true", help="end-to-end leg: upload every batch right before its own step (no overlap with the previous step)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -84,3 +84,56 @@ def test_graph_rejects_shape_change():
             step(bad)
     finally:
         o.disable_device_step()
+
+
+@pytest.mark.parametrize("wname", ["c4", "c3"])
+def test_prefetched_steps_match_plain_replays(wname):
+    """double_buffer=True: batches uploaded from pinned host memory on the copy stream into the alternate input set, replayed by the
+    alternate graph -- same losses and parameters as the single-graph replays of the same batches (dropout on: both graphs read the
+    one device step counter, so step i draws the same masks either way)."""
+    from maven_b200.graph import GraphedTrainStep
+    m_a, o_a, batches = _make(wname, 0.1)
+    m_b, o_b, _ = _make(wname, 0.1)
+    for m in (m_a, m_b):                                   # seeds mix in id(module) and a call counter: pin them so that both
+        for i, mod in enumerate(m.modules()):               # models (and both captured graphs) hash the same (seed, site, step)
+            mod.dropout_seed = 0x5EED0000 + i
+    host = [[None if v is None else v.cpu().pin_memory() for v in b] for b in batches]
+    try:
+        plain = GraphedTrainStep(m_a, o_a, batches[0])
+        losses_a = [plain(b).item() for b in batches + batches]
+        o_a.disable_device_step()
+        pre = GraphedTrainStep(m_b, o_b, batches[0], double_buffer=True)
+        seq = host + host
+        losses_b = []
+        pre.prefetch(seq[0])
+        for i in range(len(seq)):
+            loss = pre.step_prefetched()
+            if i + 1 < len(seq):
+                pre.prefetch(seq[i + 1] if i % 2 else (lambda static, b=seq[i + 1]: b))     # tuple and callable forms
+            losses_b.append(loss.item())
+        for a, b in zip(losses_a, losses_b):
+            assert abs(a - b) <= 1e-6 * abs(a), (losses_a, losses_b)
+        sd_a, sd_b = m_a.state_dict(), m_b.state_dict()
+        for k in sd_a:
+            if sd_a[k].is_floating_point():
+                assert (sd_a[k] - sd_b[k]).abs().max().item() <= 1e-6 * (1 + sd_a[k].abs().max().item()), k
+            else:
+                assert torch.equal(sd_a[k], sd_b[k]), k
+        assert o_a._steps == o_b._steps
+        with pytest.raises(RuntimeError, match="without a prefetch"):
+            pre.step_prefetched()
+        assert abs(pre(batches[1]).item()) > 0          # the plain call still works on a double-buffered step
+    finally:
+        o_a.disable_device_step()
+        o_b.disable_device_step()
+
+
+def test_prefetch_needs_double_buffer():
+    from maven_b200.graph import GraphedTrainStep
+    m, o, batches = _make("c2", 0.0)
+    try:
+        step = GraphedTrainStep(m, o, batches[0])
+        with pytest.raises(RuntimeError, match="double_buffer"):
+            step.prefetch(batches[1])
+    finally:
+        o.disable_device_step()
