@@ -37,6 +37,12 @@ WORKLOADS = {
                lc=dict(n_out=32, emb=64, heads=8, depth=5, time_norm=20583.369161312577, agg="mean"),
                sp=dict(n_out=32, emb=32, heads=2, depth=13, time_norm=17945.142213594805, agg="mean"),
                T_lc=200, T_sp=220),
+    # configs/maven-lite.yaml as shipped (BASELINE.json configs[0]): attention-pooled light curves + spectra padded to 1024
+    "c1": dict(desc="C1 maven-lite as configured: lightcurve(E64,h8,L5,T200,2 bands,agg=attn)+spectral(E32,h2,L13,T1024) CLIP",
+               combinations=["lightcurve", "spectral"], lc_dist="ztfbts", sp_dist="c1",
+               lc=dict(n_out=32, emb=64, heads=8, depth=5, time_norm=20583.369161312577, agg="attn"),
+               sp=dict(n_out=32, emb=32, heads=2, depth=13, time_norm=17945.142213594805, agg="mean"),
+               T_lc=200, T_sp=1024),
     "c2": dict(desc="C2 lc_5way_f1 shape: lightcurve(E32,h2,L9,T200) 5-way classifier",
                combinations=["lightcurve"], classification=True, n_classes=5,
                lc=dict(n_out=32, emb=32, heads=2, depth=9, time_norm=3371.17, agg="mean"), sp=None, T_lc=200, T_sp=0),
@@ -48,9 +54,13 @@ LR, WD, LOGIT_SCALE = 3.716367614864064e-05, 0.000555522900788888, 19.5459669234
 # --------------------------------------------------------------------------------------------------
 # synthetic data, generated on the CPU with a fixed seed
 # --------------------------------------------------------------------------------------------------
-def make_seq(gen, B, T, nband, lo, hi, tmax, t0, lognormal=False):
+def make_seq(gen, B, T, nband, lo, hi, tmax, t0, lognormal=False, c1_spectra=False):
     per = T // nband
-    if lognormal:     # ZTFBTS shape: n_obs per band ~ clip(round(LogNormal(ln 8, 0.7)), 1, 100)
+    if c1_spectra:    # SURVEY §8d, C1 spectra: valid length 214 (60 %), the full 1024 (30 %), Uniform{1..1024} (10 %)
+        u = torch.rand(B, nband, generator=gen)
+        n = torch.where(u < 0.6, torch.full((B, nband), min(214, per)), torch.where(u < 0.9, torch.full((B, nband), per),
+                        torch.randint(1, per + 1, (B, nband), generator=gen)))
+    elif lognormal:     # ZTFBTS shape: n_obs per band ~ clip(round(LogNormal(ln 8, 0.7)), 1, 100)
         n = torch.exp(math.log(8.0) + 0.7 * torch.randn(B, nband, generator=gen)).round().clamp(1, min(hi, per)).long()
     else:
         n = torch.randint(lo, min(hi, per) + 1, (B, nband), generator=gen)
@@ -69,7 +79,8 @@ def make_batch(wl, B, seed):
     x_lc, t_lc, m_lc = make_seq(gen, B, wl["T_lc"], 2, 20, 100, 300.0, 0.0,           # sim-pretrain shape: Uniform{20..100}/band
                                 lognormal=wl.get("lc_dist") == "ztfbts")
     if wl["sp"] is not None:
-        x_sp, t_sp, m_sp = make_seq(gen, B, wl["T_sp"], 1, 110, 220, 5500.0, 3700.0)   # valid length Uniform{110..220}
+        x_sp, t_sp, m_sp = make_seq(gen, B, wl["T_sp"], 1, 110, 220, 5500.0, 3700.0,   # valid length Uniform{110..220}
+                                    c1_spectra=wl.get("sp_dist") == "c1")
     else:
         x_sp = t_sp = m_sp = None
     cls = torch.randint(0, 5, (B,), generator=gen)
