@@ -117,6 +117,7 @@ class GraphedTrainStep:
     def copy_stream(self):
         return self._copy_stream
 
+    @ops.nvtx_range("graph.prefetch")
     def prefetch(self, batch):
         """Start the upload of the next batch into the input set the running step does not read (copy stream, asynchronous).
         `batch`: the 9-tuple, or a callable `f(static) -> batch` that is run inside the copy stream and may fill inputs on the
@@ -131,6 +132,7 @@ class GraphedTrainStep:
             self._copy_done.record(self._copy_stream)
         self._filled = tgt
 
+    @ops.nvtx_range("graph.replay")
     def step_prefetched(self) -> torch.Tensor:
         """One training step on the batch handed to the last `prefetch`."""
         if self._filled is None:
@@ -145,6 +147,7 @@ class GraphedTrainStep:
         self.optimizer.note_graph_replay()
         return loss
 
+    @ops.nvtx_range("graph.replay")
     def __call__(self, batch: Optional[Sequence[Optional[torch.Tensor]]] = None) -> torch.Tensor:
         """One training step on `batch` (None: reuse what is in the static buffers).  Returns the loss (device tensor,
         overwritten by the next call)."""

@@ -11,7 +11,9 @@ untouched); backward writes one flat gradient buffer and hands autograd per-para
 from __future__ import annotations
 
 import ctypes
+import functools
 import math
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -29,6 +31,28 @@ def launches() -> int:
 def _count(n: int):
     global _LAUNCHES
     _LAUNCHES += n
+
+
+# NVTX ranges: MVN_NVTX=1 brackets every library call group (encoder / ConvMixer / loss forward and backward, optimizer,
+# graph replay) with a named range so that a timeline (nsys, ncu --nvtx) reads in the reference's terms.  Off by default: no cost.
+_NVTX = os.environ.get("MVN_NVTX", "0") == "1"
+
+
+def nvtx_range(name: str):
+    """Decorator: run the function inside the NVTX range `maven/<name>` when MVN_NVTX=1."""
+    def deco(fn):
+        if not _NVTX:
+            return fn
+
+        @functools.wraps(fn)
+        def wrapped(*a, **k):
+            torch.cuda.nvtx.range_push("maven/" + name)
+            try:
+                return fn(*a, **k)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return wrapped
+    return deco
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -123,6 +147,7 @@ class SeqEncoderFn(torch.autograd.Function):
     parameters (only so that autograd routes their gradients; the kernels read the flat buffer)."""
 
     @staticmethod
+    @nvtx_range("seq_encoder.forward")
     def forward(ctx, x, t, mask, call: SeqCall, *params):
         L = lib()
         x = _req(x, "x"); t = _req(t, "t")
@@ -150,6 +175,7 @@ class SeqEncoderFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @nvtx_range("seq_encoder.backward")
     def backward(ctx, dout):
         L = lib()
         dout = _req(dout, "grad_output")
@@ -185,6 +211,7 @@ class LinearFn(torch.autograd.Function):
     """Y = X W^T + b over the last dimension (nn.Linear)."""
 
     @staticmethod
+    @nvtx_range("linear.forward")
     def forward(ctx, x, w, b, prec: int):
         L = lib()
         shp = x.shape
@@ -200,6 +227,7 @@ class LinearFn(torch.autograd.Function):
         return y.view(*shp[:-1], N)
 
     @staticmethod
+    @nvtx_range("linear.backward")
     def backward(ctx, dy):
         L = lib()
         x2, w = ctx.saved_tensors
@@ -230,6 +258,7 @@ class LinearReluFn(torch.autograd.Function):
     """relu(X W^T + b) (MLP heads): fused ReLU epilogue forward, mask + the two GEMMs backward."""
 
     @staticmethod
+    @nvtx_range("linear_relu.forward")
     def forward(ctx, x, w, b, prec: int):
         L = lib()
         shp = x.shape
@@ -244,6 +273,7 @@ class LinearReluFn(torch.autograd.Function):
         return h.view(*shp[:-1], N)
 
     @staticmethod
+    @nvtx_range("linear_relu.backward")
     def backward(ctx, dh):
         L = lib()
         x2, w, h = ctx.saved_tensors
@@ -351,6 +381,7 @@ class LinearResLNFn(torch.autograd.Function):
     """Y = LayerNorm(X W^T + b + R) gamma + beta (one kernel); backward = LN-bwd, dX GEMM, dW GEMM."""
 
     @staticmethod
+    @nvtx_range("linear_res_ln.forward")
     def forward(ctx, x, w, b, r, gamma, beta, eps: float, prec: int):
         L = lib()
         shp = r.shape
@@ -369,6 +400,7 @@ class LinearResLNFn(torch.autograd.Function):
         return y.view(shp)
 
     @staticmethod
+    @nvtx_range("linear_res_ln.backward")
     def backward(ctx, dy):
         L = lib()
         x2, w, xhat, rstd, gamma = ctx.saved_tensors
@@ -394,6 +426,7 @@ class FFNResLNFn(torch.autograd.Function):
     """Y = LayerNorm(relu(X W1^T + b1) W2^T + b2 + X) gamma + beta  -- the feed-forward half of a TransformerBlock."""
 
     @staticmethod
+    @nvtx_range("ffn_res_ln.forward")
     def forward(ctx, x, w1, b1, w2, b2, gamma, beta, eps: float, prec: int):
         L = lib()
         shp = x.shape
@@ -414,6 +447,7 @@ class FFNResLNFn(torch.autograd.Function):
         return y.view(shp)
 
     @staticmethod
+    @nvtx_range("ffn_res_ln.backward")
     def backward(ctx, dy):
         L = lib()
         x2, w1, w2, h, xhat, rstd, gamma = ctx.saved_tensors
@@ -442,6 +476,7 @@ class AttentionFn(torch.autograd.Function):
     """Packed padding-masked attention core on qkv (M,3E) with dense plan (all B*T rows, keys masked)."""
 
     @staticmethod
+    @nvtx_range("attention.forward")
     def forward(ctx, qkv, mask, B: int, T: int, E: int, H: int):
         L = lib()
         qkv2 = _req(qkv, "qkv").reshape(B * T, 3 * E)
@@ -461,6 +496,7 @@ class AttentionFn(torch.autograd.Function):
         return out.view(B, T, E)
 
     @staticmethod
+    @nvtx_range("attention.backward")
     def backward(ctx, dout):
         L = lib()
         qkv2, cu, kv, out, lse = ctx.saved_tensors
@@ -486,6 +522,7 @@ class ConvMixerFn(torch.autograd.Function):
     batch sums are all-reduced between stages (SyncBN semantics: statistics of the GLOBAL batch)."""
 
     @staticmethod
+    @nvtx_range("convmixer.forward")
     def forward(ctx, x, call: ConvCall, *params):
         from ._lib import ConvCfg
         L = lib()
@@ -532,6 +569,7 @@ class ConvMixerFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @nvtx_range("convmixer.backward")
     def backward(ctx, dout):
         L = lib()
         dout = _req(dout, "grad_output")
@@ -602,6 +640,7 @@ class AttnPoolFn(torch.autograd.Function):
     B*T tokens of the per-op path is never formed."""
 
     @staticmethod
+    @nvtx_range("attn_pool.forward")
     def forward(ctx, tokens, mask, query, in_w, in_b, out_w, out_b, H: int):
         L = lib()
         tokens = _req(tokens, "tokens")
@@ -617,6 +656,7 @@ class AttnPoolFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @nvtx_range("attn_pool.backward")
     def backward(ctx, dout):
         L = lib()
         tokens, m, query, in_w, in_b, out_w, out_b, saved = ctx.saved_tensors
@@ -742,6 +782,7 @@ class ClipLossFn(torch.autograd.Function):
     above.  (tests/test_dp_gloo.py drives this protocol on two CPU processes with test-side torch stand-ins for the two kernels.)"""
 
     @staticmethod
+    @nvtx_range("clip_loss.forward")
     def forward(ctx, e1, e2, logit_scale, logit_bias, prec: int):
         if e1.shape != e2.shape or e1.dim() != 2:
             raise ValueError(f"clip_loss: embeddings must both be (N, D), got {tuple(e1.shape)} and {tuple(e2.shape)}")
@@ -768,6 +809,7 @@ class ClipLossFn(torch.autograd.Function):
         return loss.reshape(())
 
     @staticmethod
+    @nvtx_range("clip_loss.backward")
     def backward(ctx, g):
         e1, e2, e1_all, e2_all, ls, lb, lse_all = ctx.saved_tensors
         n, N, D, off, prec, ls_shape, lb_shape = ctx.meta
@@ -785,6 +827,7 @@ class ClipLossMultiFn(torch.autograd.Function):
     the same two kernels per pair as ClipLossFn."""
 
     @staticmethod
+    @nvtx_range("clip_loss_multimodal.forward")
     def forward(ctx, logit_scale, logit_bias, prec: int, *embs):
         M = len(embs)
         n, D = embs[0].shape
@@ -820,6 +863,7 @@ class ClipLossMultiFn(torch.autograd.Function):
         return total.reshape(())
 
     @staticmethod
+    @nvtx_range("clip_loss_multimodal.backward")
     def backward(ctx, g):
         e_loc, e_all, ls, lb, lse_all = ctx.saved_tensors
         M, n, N, D, off, prec, pairs, ls_shape, lb_shape = ctx.meta

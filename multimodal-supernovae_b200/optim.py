@@ -119,6 +119,7 @@ class FusedRAdam(torch.optim.Optimizer):
             self._steps = [0] * len(g.params)
 
     @torch.no_grad()
+    @ops.nvtx_range("radam.step")
     def step(self, closure=None):
         loss = None
         if closure is not None:

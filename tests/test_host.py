@@ -4,6 +4,7 @@ names, and the product path refuses CPU tensors instead of falling back."""
 import ctypes
 import os
 import re
+import sys
 
 import pytest
 import torch
@@ -205,3 +206,16 @@ def test_pretraining_masks_match_reference_golden():
     assert torch.equal(m_in, g["cont_in"]) and torch.equal(m_pred, g["cont_pred"])
     # every selected position is valid, the two masks partition the padding mask
     assert torch.equal(m_in | m_pred, g["mask"]) and not (m_in & m_pred).any()
+
+
+def test_nvtx_ranges_are_opt_in():
+    """MVN_NVTX=1 wraps the library call groups in named NVTX ranges; without it the functions are left untouched (no cost)."""
+    import subprocess
+    code = ("import sys; sys.path.insert(0, %r); import maven_b200.ops as o, maven_b200.graph as g, maven_b200.optim as r; "
+            "print(hasattr(o.SeqEncoderFn.forward, '__wrapped__'), hasattr(o.ClipLossMultiFn.backward, '__wrapped__'), "
+            "hasattr(g.GraphedTrainStep.__call__, '__wrapped__'), hasattr(r.FusedRAdam.step, '__wrapped__'))" % ROOT)
+    for flag, want in (("1", "True True True True"), ("0", "False False False")):
+        env = dict(os.environ, MVN_NVTX=flag)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-400:]
+        assert out.stdout.strip().startswith(want), (flag, out.stdout)
