@@ -121,7 +121,9 @@ class GraphedTrainStep:
     def prefetch(self, batch):
         """Start the upload of the next batch into the input set the running step does not read (copy stream, asynchronous).
         `batch`: the 9-tuple, or a callable `f(static) -> batch` that is run inside the copy stream and may fill inputs on the
-        device itself (e.g. an 8-bit image upload + augment_images(out=static[0])), returning those same tensors in the batch."""
+        device itself (e.g. an 8-bit image upload + augment_images(out=static[0])), returning those same tensors in the batch.
+        Sources are host tensors (pinned, for the copy to be asynchronous) or device tensors that are already complete: the copy
+        stream does NOT wait for work queued on the caller's stream -- it would queue behind the running step and lose the overlap."""
         static = self.prefetch_buffers()
         tgt = self._cur ^ 1
         self._copy_stream.wait_event(self._read_done[tgt])       # only the replay that last READ this set: the running step reads the other one
