@@ -19,7 +19,13 @@ VARIANTS = {
     "split_aux_delay": ["EXP_SPLIT_AUX", "EXP_DELAY_FIRST_FILL"],
     "split_aux_fence": ["EXP_SPLIT_AUX", "EXP_FENCE_AFTER_WAIT"],
     "split_aux_after_a": ["EXP_SPLIT_AUX", "EXP_AUX_AFTER_A"],
+    "split_aux_reread": ["EXP_SPLIT_AUX", "EXP_REREAD"],              # marks rows whose slot content changed after the wait returned
+    "split_aux_swap": ["EXP_SPLIT_AUX", "EXP_SWAP_GROUPS"],
+    "split_aux_dep_arrive": ["EXP_SPLIT_AUX", "EXP_DEP_ARRIVE"],      # release the slot only after the row loads have returned
+    "split_aux_delay_after_release": ["EXP_SPLIT_AUX", "EXP_DELAY_AFTER_RELEASE"],   # early refill, late output: which side matters?           # group 1 reads slot 0 first: does the failure follow the group or the slot?
 }
+if os.environ.get("EXP_ONLY"):
+    VARIANTS = {k: v for k, v in VARIANTS.items() if k in os.environ["EXP_ONLY"].split(",")}
 
 
 def main():
@@ -28,7 +34,8 @@ def main():
     try:
         for name, defs in VARIANTS.items():
             head = "".join(f"#define {d} 1\n" for d in defs)
-            open(SRC, "w").write(head + exp)
+            # the round-1 file predates tc_trunc_comp() (ffn_fused.cu links against it): the variants run without the compensation
+            open(SRC, "w").write(head + exp + "\nnamespace mvn { float tc_trunc_comp() { return 1.0f; } }\n")
             r = subprocess.run([sys.executable, os.path.join(ROOT, "__graft_entry__.py")], capture_output=True, text=True)
             if "built" not in r.stdout:
                 sys.stderr.write(r.stderr[-2000:])

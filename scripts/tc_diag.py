@@ -22,7 +22,7 @@ for (M, N, K, mode) in [(60001, 64, 256, "addend")] * REPS + [(60001, 64, 256, "
     torch.cuda.synchronize()
     d = (dx.cpu().double() - ref).abs()
     bad = d > 0.05
-    print(M, N, K, mode, "rc", rc, "bad frac", bad.float().mean().item(), "nan", torch.isnan(dx).sum().item())
+    print(M, N, K, mode, "rc", rc, "bad frac", bad.float().mean().item(), "nan", torch.isnan(dx).sum().item(), "marks", (dx.abs() > 1e5).sum().item())
     if bad.any():
         tiles = bad.view(-1)[: (M // 128) * 128 * K].view(M // 128, 128, K // 32, 32).any(dim=3).any(dim=1)   # [tile, chunk]
         bt = tiles.any(dim=1).nonzero().flatten()
@@ -31,6 +31,16 @@ for (M, N, K, mode) in [(60001, 64, 256, "addend")] * REPS + [(60001, 64, 256, "
         t0 = int(bt[0]); r = bad[t0 * 128:(t0 + 1) * 128].any(dim=1).nonzero().flatten()
         print("  bad rows in tile", t0, ":", r.tolist(), "count", len(r))
         if mode == "addend":
+            # where does the garbage come from?  Search every (tile, chunk) of the expected OUTPUT and of the aux tensor, same row of the box
+            ch0 = int(tiles[t0].nonzero().flatten()[0])
+            nt, nc = M // 128, K // 32
+            ref4 = ref[: nt * 128].view(nt, 128, nc, 32); add4 = add.double()[: nt * 128].view(nt, 128, nc, 32)
+            base4 = (dy.double() @ w.double())[: nt * 128].view(nt, 128, nc, 32)
+            for row in r[:4].tolist():
+                got = dx[t0 * 128 + row, ch0 * 32:(ch0 + 1) * 32].cpu().double()
+                for name, cand in (("output", ref4[:, row]), ("aux", add4[:, row]), ("gemm", base4[:, row]), ("aux-part", add4[:, row] + base4[t0, row, ch0])):
+                    e = (cand - got).abs().amax(dim=-1)                       # [tile, chunk]
+                    i = int(e.argmin()); print("    row", row, "best match in", name, "-> tile", i // nc, "chunk", i % nc, "err %.2e" % e.view(-1)[i].item())
             ch = int(tiles[t0].nonzero().flatten()[0])
             base = (dy.double() @ w.double())
             for row in r[:6].tolist():
