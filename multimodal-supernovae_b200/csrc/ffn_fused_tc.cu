@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) tc_ffn_fwd_kernel(const __grid_
                 for (int j = 0; j < 32; ++j) z[ec][j] += b2s[ec * 32 + j] + xr[j];
             }
             tc_fence_before();
+            fence_proxy_async();          // the residual rows were read through the generic proxy: order them before the next TMA write of the x tile (see gemm_tc.cu::aux_row)
             __syncwarp();
             if (lane == 0) { mbar_arrive(out_empty); mbar_arrive(x_empty); }     // accumulator drained, residual tile read: next tile may load
             float sum = 0.f;

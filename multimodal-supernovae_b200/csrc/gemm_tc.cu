@@ -316,6 +316,11 @@ __global__ void __launch_bounds__(32 * (EPI_WARP0 + NUM_EPI_WARPS * EG), 1) tc_g
             const int s = xit % nX;
             mbar_wait(xfull_bar(s), (xit / nX) & 1);
             box_row_read(smem + OFF_A + (nA + s) * STAGE_BYTES, quad * 32 + lane, r);
+            // The release hands the slot to the async proxy (the producer's next TMA write).  Without a proxy fence the compiler issues
+            // SYNCS.ARRIVE while the eight row loads are still in flight, and a refill that lands early is read by the later loads: a
+            // write-after-read race across proxies, observed as rows that mix two fills when both epilogue groups released the first
+            // slots at once (profiles/r02c_aux_ring_experiments.md).  The fence orders this thread's reads before the release.
+            fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(xempty_bar(s));
             ++xit;

@@ -21,6 +21,7 @@ VARIANTS = {
     "split_aux_after_a": ["EXP_SPLIT_AUX", "EXP_AUX_AFTER_A"],
     "split_aux_reread": ["EXP_SPLIT_AUX", "EXP_REREAD"],              # marks rows whose slot content changed after the wait returned
     "split_aux_swap": ["EXP_SPLIT_AUX", "EXP_SWAP_GROUPS"],
+    "split_aux_fence_release": ["EXP_SPLIT_AUX", "EXP_FENCE_BEFORE_RELEASE"],   # the fix: reads ordered before the release
     "split_aux_dep_arrive": ["EXP_SPLIT_AUX", "EXP_DEP_ARRIVE"],      # release the slot only after the row loads have returned
     "split_aux_delay_after_release": ["EXP_SPLIT_AUX", "EXP_DELAY_AFTER_RELEASE"],   # early refill, late output: which side matters?           # group 1 reads slot 0 first: does the failure follow the group or the slot?
 }

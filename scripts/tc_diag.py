@@ -30,6 +30,34 @@ for (M, N, K, mode) in [(60001, 64, 256, "addend")] * REPS + [(60001, 64, 256, "
         print("  bad chunks in first bad tiles:", [tiles[t].nonzero().flatten().tolist() for t in bt[:6]])
         t0 = int(bt[0]); r = bad[t0 * 128:(t0 + 1) * 128].any(dim=1).nonzero().flatten()
         print("  bad rows in tile", t0, ":", r.tolist(), "count", len(r))
+        # which columns of a bad row are wrong (one character per 16-byte chunk of the 128-byte row: x = wrong), and, for the ReLU-mask
+        # mode (output = gemm or 0), whether a wrong element is a flipped mask (the aux row was wrong) or neither value (accumulator / box)
+        base_full = dy.double() @ w.double()
+        ch0 = int(tiles[t0].nonzero().flatten()[0])
+        for row in r[:6].tolist():
+            gr = t0 * 128 + row
+            e = d[gr, ch0 * 32:(ch0 + 1) * 32] > 0.05
+            print("    row", row, "chunk", ch0, "wrong 16-byte chunks:", "".join("x" if e[4 * q:4 * q + 4].any() else "." for q in range(8)), "wrong elements", int(e.sum()))
+        if mode == "addend":
+            # element-wise: do the WRONG elements of a row carry the aux values of a LATER fill of the same ring slot (chunk ch0 + 4k of this
+            # tile, or a chunk of the CTA's next tile)?  Then the row was read while / after the slot was being refilled.
+            for row in r[:6].tolist():
+                gr = t0 * 128 + row
+                e = d[gr, ch0 * 32:(ch0 + 1) * 32] > 0.05
+                used = dx[gr, ch0 * 32:(ch0 + 1) * 32].cpu().double() - base_full[gr, ch0 * 32:(ch0 + 1) * 32]
+                hits = []
+                for tt in (t0, t0 + 148):
+                    if (tt + 1) * 128 > M: continue
+                    for cc in range(K // 32):
+                        cand = add[tt * 128 + row, cc * 32:(cc + 1) * 32].double()
+                        if ((cand - used).abs()[e] < 1e-3).all(): hits.append((tt - t0, cc))
+                print("    row", row, ": the", int(e.sum()), "wrong elements equal aux[(tile offset, chunk)] =", hits if hits else "nothing in this CTA's two first tiles")
+        if mode == "relu_mask":
+            got = dx.cpu().double()
+            flipped_off = (bad & (got.abs() < 1e-6)).sum().item()
+            flipped_on = (bad & ((got - base_full).abs() < 0.05) & (ref == 0)).sum().item()
+            print("    relu_mask: wrong elements", int(bad.sum()), "of which masked though src > 0:", flipped_off, ", passed though src <= 0:", flipped_on,
+                  ", neither 0 nor the gemm value:", int(bad.sum()) - flipped_off - flipped_on)
         if mode == "addend":
             # where does the garbage come from?  Search every (tile, chunk) of the expected OUTPUT and of the aux tensor, same row of the box
             ch0 = int(tiles[t0].nonzero().flatten()[0])
