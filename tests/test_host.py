@@ -219,3 +219,46 @@ def test_nvtx_ranges_are_opt_in():
         out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
         assert out.returncode == 0, out.stderr[-400:]
         assert out.stdout.strip().startswith(want), (flag, out.stdout)
+
+
+def _sass_functions(lib_path, name_filter):
+    """{function name: [instruction text, ...]} of the sm_100a SASS in `lib_path` for functions whose mangled name contains `name_filter`."""
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([exe, "-sass", lib_path], capture_output=True, text=True, timeout=600).stdout
+    funcs, cur = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1) if name_filter in m.group(1) else None
+            if cur:
+                funcs[cur] = []
+            continue
+        m = re.match(r"\s*/\*[0-9a-f]+\*/\s+(.*?);", line)
+        if cur and m:
+            funcs[cur].append(m.group(1).strip())
+    return funcs
+
+
+def test_tma_slot_release_is_fenced_after_generic_reads(built):
+    """A shared-memory slot that TMA refills may only be released (mbarrier arrive) after the generic-proxy loads that read it have been
+    ordered by a proxy fence: in SASS, no `SYNCS.ARRIVE` within a few instructions of a group of `LD.E.128` row loads without a
+    `FENCE.VIEW.ASYNC` in between.  Without it the arrive issues with the loads in flight and an early refill is read by the later loads
+    (profiles/r02c_aux_ring_experiments.md: 11 / 20 failing runs -> 0 / 20)."""
+    lib_path = os.path.join(ROOT, "multimodal-supernovae_b200", "libmaven_sm100.so")
+    checked = 0
+    for pat in ("tc_gemm_kernel", "tc_ffn_fwd_kernel"):
+        for name, ins in _sass_functions(lib_path, pat).items():
+            for i, text in enumerate(ins):
+                if "SYNCS.ARRIVE" not in text or "A1T0" not in text:
+                    continue
+                window = ins[max(0, i - 12):i]
+                loads = [k for k, t in enumerate(window) if t.split()[0].lstrip("@!P0123456 ").startswith(("LD.E.128", "LDS.128"))]
+                if not loads:
+                    continue
+                checked += 1
+                assert any("FENCE.VIEW.ASYNC" in t for t in window[loads[-1]:]), f"{name}: release at instruction {i} right after row loads without a proxy fence"
+    assert checked >= 2, "the aux-row / residual-row release sites were not found in the SASS (did the kernels change shape?)"
