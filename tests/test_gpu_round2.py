@@ -186,3 +186,35 @@ def test_masked_lc_pretraining_golden():
     assert torch.equal(loss9, loss)
     xs, ps = m.masked_pred(x, t, mask, f_mask=0.25)
     assert xs.shape == ps.shape and xs.ndim == 1
+
+
+@pytest.mark.parametrize("tier,tol", [("fp32", TOL), ("fused", 1e-3)])
+def test_c1_shape_golden(tier, tol):
+    """BASELINE.json configs[0] (configs/maven-lite.yaml as shipped: agg="attn" light curves, spectra padded to 1024 tokens) against the
+    fixture written by the unmodified reference (tests/golden/make_golden_c1.py): loss, gradients (fp32 tier) and eval embeddings."""
+    from maven_b200.models_multimodal import LightCurveImageCLIP
+    from maven_b200.transformer_utils import set_precision
+    g = load_golden("model_c1")
+    tk = dict(n_out=32, emb=64, heads=8, depth=2, dropout=0.0, time_norm=20583.369161312577, agg="attn")
+    sk = dict(n_out=32, emb=32, heads=2, depth=3, dropout=0.0, time_norm=17945.142213594805, agg="mean")
+    m = LightCurveImageCLIP(logit_scale=19.545966923442453, lr=1e-3, nband=2, loss="softmax", transformer_kwargs=tk, transformer_spectral_kwargs=sk,
+                            optimizer_kwargs={"weight_decay": 5.6e-4}, combinations=["lightcurve", "spectral"])
+    sd, grads, _ = split_golden(g)
+    for k in ("logit_scale", "logit_bias"):
+        sd[k] = g[k]
+    m.load_state_dict(sd)
+    m = set_precision(m.to(dev()).train(), tier)
+    loss = m.training_step(_batch(g), 0)
+    assert abs(loss.item() - g["loss"].item()) < tol * abs(g["loss"].item())
+    loss.backward()
+    for k, p in m.named_parameters():
+        got = p.grad if p.grad is not None else torch.zeros_like(p)
+        if tier == "fp32":
+            assert relerr(got, grads[k]) < GTOL or (got.cpu() - grads[k]).abs().max() < 1e-7, k
+        else:
+            assert torch.isfinite(got).all(), k
+    m.eval()
+    with torch.no_grad():
+        out = m(*_batch(g))
+    for i, o in enumerate(out):
+        assert relerr(o, g[f"eval_out{i}"]) < tol

@@ -224,3 +224,30 @@ def test_masked_lc_pretraining_objective():
     for k, ref in grads.items():
         got = sd[k].grad if sd[k].grad is not None else torch.zeros_like(ref)
         assert relerr(got, ref) < 5e-5 or (got - ref).abs().max() < 1e-6, k
+
+
+C1_CFG = dict(nband=2, combinations=["lightcurve", "spectral"],
+              transformer_kwargs=dict(n_out=32, emb=64, heads=8, depth=2, time_norm=20583.369161312577, agg="attn"),
+              transformer_spectral_kwargs=dict(n_out=32, emb=32, heads=2, depth=3, time_norm=17945.142213594805, agg="mean"))
+
+
+def test_training_step_c1_shape():
+    """BASELINE.json configs[0] (configs/maven-lite.yaml as shipped): attention-pooled light curves (nn.MultiheadAttention over the
+    zero-padded rows) + spectra padded to 1024 tokens with lengths 214 / 1024 / 517 / 214 -- loss, every gradient and the eval
+    embeddings of the unmodified reference (tests/golden/make_golden_c1.py)."""
+    g = load_golden("model_c1")
+    sd, grads, _ = split_golden(g)
+    for k in ("logit_scale", "logit_bias"):
+        sd[k] = g[k]
+    sd = _leafify(sd)
+    batch = (None, g["x_lc"], g["t_lc"], g["mask_lc"], g["x_sp"], g["t_sp"], g["mask_sp"], g["redshift"], g["cls"])
+    loss = O.training_loss(sd, C1_CFG, batch)
+    assert abs(loss.item() - g["loss"].item()) < 2e-6 * abs(g["loss"].item())
+    loss.backward()
+    for k, ref in grads.items():
+        got = sd[k].grad if sd[k].grad is not None else torch.zeros_like(ref)
+        assert relerr(got, ref) < 2e-4 or (got - ref).abs().max() < 1e-7, k
+    with torch.no_grad():
+        out = O.model_forward({k: v.detach() for k, v in sd.items()}, C1_CFG, batch, training=False)
+    for i, o in enumerate(out):
+        assert relerr(o, g[f"eval_out{i}"]) < 1e-5
